@@ -1,0 +1,502 @@
+// Forward kernels of the YuNet hot path, fp32 NHWC, sm_100a.
+//
+//   unit_fwd_kernel  — one fused ConvDPUnit (mmdet/models/utils/yunet_layer.py:30-36):
+//       load prologue: a = relu(bn(z_in)) [+ 2x2 max-pool (yunet_backbone.py:40) | + nearest-up2
+//       add (tfpn.py:39-40)] -> pointwise 1x1 GEMM (+bias) on the halo tile -> depthwise 3x3
+//       stencil (+bias) from shared memory -> store pre-BN z once + per-channel sum / sum^2
+//       (train-mode BatchNorm statistics, applied by the *consumer's* prologue).
+//   stem_fwd_kernel  — Conv_head.conv1: dense 3x3 stride-2 conv 3->16 (yunet_layer.py:51,58),
+//       reads NCHW input, writes NHWC pre-BN + statistics.
+//   bn_update_running_kernel — running_mean / running_var update (torch BatchNorm2d, momentum,
+//       unbiased variance) for all BatchNorm layers in one launch.
+//
+// The pointwise GEMM here is the fp32 CUDA-core version (exact fp32, the parity baseline);
+// the tcgen05 3xTF32 version for the 64-channel units lives in unit_fwd_tc.cu.
+#include <cstdio>
+
+#include "kernels.h"
+
+namespace yunet {
+
+namespace {
+
+constexpr int TH = 8, TW = 16;              // output tile
+constexpr int HH = TH + 2, HW = TW + 2;     // halo tile
+constexpr int HP = HH * HW;                 // 180 halo pixels
+constexpr int HPP = 192;                    // padded to the GEMM's pixel blocking
+constexpr int NT = 256;
+
+__device__ __forceinline__ void bn_coeffs(const BnRef& r, int c, float& scale, float& shift) {
+  float m, v;
+  if (r.train) {
+    double dm = r.sum[c] * r.inv_count;
+    double dv = r.sumsq[c] * r.inv_count - dm * dm;
+    if (dv < 0.0) dv = 0.0;
+    m = (float)dm;
+    v = (float)dv;
+  } else {
+    m = r.rmean[c];
+    v = r.rvar[c];
+  }
+  float rstd = 1.0f / sqrtf(v + kBnEps);
+  scale = r.gamma[c] * rstd;
+  shift = r.beta[c] - m * scale;
+}
+
+__device__ __forceinline__ float4 bn_relu4(float4 z, float4 sc, float4 sh) {
+  float4 r;
+  r.x = fmaxf(fmaf(z.x, sc.x, sh.x), 0.f);
+  r.y = fmaxf(fmaf(z.y, sc.y, sh.y), 0.f);
+  r.z = fmaxf(fmaf(z.z, sc.z, sh.z), 0.f);
+  r.w = fmaxf(fmaf(z.w, sc.w, sh.w), 0.f);
+  return r;
+}
+__device__ __forceinline__ float4 max4(float4 a, float4 b) {
+  return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
+}
+__device__ __forceinline__ float4 add4(float4 a, float4 b) {
+  return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+__device__ __forceinline__ void fma4(float4& acc, float4 w, float4 v) {
+  acc.x = fmaf(w.x, v.x, acc.x);
+  acc.y = fmaf(w.y, v.y, acc.y);
+  acc.z = fmaf(w.z, v.z, acc.z);
+  acc.w = fmaf(w.w, v.w, acc.w);
+}
+__device__ __forceinline__ float4 ldg4(const float* p) {
+  return __ldg(reinterpret_cast<const float4*>(p));
+}
+
+template <int CIN, int COUT>
+struct FwdCfg {
+  static constexpr int CPT = (COUT == 16) ? 4 : 8;   // output channels per thread in the GEMM
+  static constexpr int NCG = COUT / CPT;             // channel groups
+  static constexpr int NPG = NT / NCG;               // pixel groups
+  static constexpr int PPT = HPP / NPG;              // pixels per thread
+  static constexpr int AS = CIN + 4;                 // sA row stride (floats)
+  static constexpr int R0 = (HPP * AS > HP * COUT) ? HPP * AS : HP * COUT;  // sA / sY union
+  static constexpr int NQ = COUT / 4;                // channel quads (dw stage)
+  static constexpr int RG = NT / (NQ * TW);          // row groups
+  static constexpr int RPT = TH / RG;                // rows per thread
+  static constexpr int SMEM_FLOATS = R0 + CIN * COUT + 9 * COUT + 2 * COUT + 4 * CIN + NT * 8;
+  static_assert(HPP % NPG == 0, "pixel blocking");
+  static_assert(NQ * TW * RG == NT && RG * RPT == TH, "dw mapping");
+};
+
+template <int CIN, int COUT, int MODE>
+__global__ void __launch_bounds__(NT, 2) unit_fwd_kernel(const UnitFwdArgs a) {
+  using C = FwdCfg<CIN, COUT>;
+  extern __shared__ float4 smem_raw[];
+  float* smem = reinterpret_cast<float*>(smem_raw);
+  float* sA = smem;                       // [HPP][AS]
+  float* sY = smem;                       // [HP][COUT]   (aliases sA after the GEMM)
+  float* sW1t = smem + C::R0;             // [CIN][COUT]
+  float* sW2 = sW1t + CIN * COUT;         // [9][COUT]
+  float* sB1 = sW2 + 9 * COUT;            // [COUT]
+  float* sB2 = sB1 + COUT;                // [COUT]
+  float* sScA = sB2 + COUT;               // [CIN]
+  float* sShA = sScA + CIN;
+  float* sScB = sShA + CIN;
+  float* sShB = sScB + CIN;
+  float* sRed = sShB + CIN;               // [NT][8]
+
+  const int tid = threadIdx.x;
+  const int tiles_x = (a.W + TW - 1) / TW;
+  const int tiles_y = (a.H + TH - 1) / TH;
+  int t = blockIdx.x;
+  const int tx = t % tiles_x; t /= tiles_x;
+  const int ty = t % tiles_y;
+  const int b = t / tiles_y;
+  const int x0 = tx * TW, y0 = ty * TH;
+
+  // ---- stage 0: weights + BN coefficients into shared memory
+  for (int i = tid; i < CIN * COUT; i += NT) {
+    int ci = i / COUT, co = i % COUT;
+    sW1t[i] = __ldg(a.w1 + co * CIN + ci);
+  }
+  for (int i = tid; i < 9 * COUT; i += NT) {
+    int k = i / COUT, co = i % COUT;
+    sW2[i] = __ldg(a.w2 + co * 9 + k);
+  }
+  if (tid < COUT) { sB1[tid] = __ldg(a.b1 + tid); sB2[tid] = __ldg(a.b2 + tid); }
+  if (tid < CIN) {
+    float sc, sh;
+    bn_coeffs(a.bna, tid, sc, sh);
+    sScA[tid] = sc; sShA[tid] = sh;
+    if (MODE == 2) {
+      bn_coeffs(a.bnb, tid, sc, sh);
+      sScB[tid] = sc; sShB[tid] = sh;
+    }
+  }
+  __syncthreads();
+
+  // ---- stage 1: halo tile of activated inputs -> sA
+  {
+    constexpr int Q = CIN / 4;
+    for (int i = tid; i < HPP * Q; i += NT) {
+      const int pix = i / Q, q = i % Q;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (pix < HP) {
+        const int hy = pix / HW, hx = pix % HW;
+        const int gy = y0 + hy - 1, gx = x0 + hx - 1;
+        if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) {
+          const float4 sc = *reinterpret_cast<const float4*>(sScA + q * 4);
+          const float4 sh = *reinterpret_cast<const float4*>(sShA + q * 4);
+          if (MODE == 0) {
+            const float* p = a.za + (((long long)b * a.H + gy) * a.W + gx) * CIN + q * 4;
+            v = bn_relu4(ldg4(p), sc, sh);
+          } else if (MODE == 1) {
+            const int W2 = a.W * 2;
+            const float* p = a.za + (((long long)b * (a.H * 2) + gy * 2) * W2 + gx * 2) * CIN + q * 4;
+            float4 v00 = bn_relu4(ldg4(p), sc, sh);
+            float4 v01 = bn_relu4(ldg4(p + CIN), sc, sh);
+            float4 v10 = bn_relu4(ldg4(p + (long long)W2 * CIN), sc, sh);
+            float4 v11 = bn_relu4(ldg4(p + (long long)W2 * CIN + CIN), sc, sh);
+            v = max4(max4(v00, v01), max4(v10, v11));
+          } else {
+            const float* p = a.za + (((long long)b * a.H + gy) * a.W + gx) * CIN + q * 4;
+            v = bn_relu4(ldg4(p), sc, sh);
+            const int Hb = a.H >> 1, Wb = a.W >> 1;
+            const float* pb = a.zb + (((long long)b * Hb + (gy >> 1)) * Wb + (gx >> 1)) * CIN + q * 4;
+            const float4 scb = *reinterpret_cast<const float4*>(sScB + q * 4);
+            const float4 shb = *reinterpret_cast<const float4*>(sShB + q * 4);
+            v = add4(v, bn_relu4(ldg4(pb), scb, shb));
+          }
+        }
+      }
+      *reinterpret_cast<float4*>(sA + pix * C::AS + q * 4) = v;
+    }
+  }
+  __syncthreads();
+
+  // ---- stage 2: pointwise GEMM  y[p][co] = sum_ci a[p][ci] * W1[co][ci]
+  const int cg = tid % C::NCG;
+  const int pg = tid / C::NCG;
+  float acc[C::PPT][C::CPT];
+#pragma unroll
+  for (int i = 0; i < C::PPT; ++i)
+#pragma unroll
+    for (int j = 0; j < C::CPT; ++j) acc[i][j] = 0.f;
+
+#pragma unroll 2
+  for (int k4 = 0; k4 < CIN / 4; ++k4) {
+    float4 av[C::PPT];
+#pragma unroll
+    for (int i = 0; i < C::PPT; ++i)
+      av[i] = *reinterpret_cast<const float4*>(sA + (pg + i * C::NPG) * C::AS + k4 * 4);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      float wv[C::CPT];
+#pragma unroll
+      for (int j4 = 0; j4 < C::CPT / 4; ++j4) {
+        float4 w = *reinterpret_cast<const float4*>(sW1t + (k4 * 4 + kk) * COUT + cg * C::CPT + j4 * 4);
+        wv[j4 * 4 + 0] = w.x; wv[j4 * 4 + 1] = w.y; wv[j4 * 4 + 2] = w.z; wv[j4 * 4 + 3] = w.w;
+      }
+#pragma unroll
+      for (int i = 0; i < C::PPT; ++i) {
+        const float ak = kk == 0 ? av[i].x : kk == 1 ? av[i].y : kk == 2 ? av[i].z : av[i].w;
+#pragma unroll
+        for (int j = 0; j < C::CPT; ++j) acc[i][j] = fmaf(ak, wv[j], acc[i][j]);
+      }
+    }
+  }
+  __syncthreads();   // every read of sA is done; the region becomes sY
+
+  // y (+bias) for in-image pixels, exact zero outside (the depthwise conv zero-pads y)
+#pragma unroll
+  for (int i = 0; i < C::PPT; ++i) {
+    const int pix = pg + i * C::NPG;
+    if (pix < HP) {
+      const int hy = pix / HW, hx = pix % HW;
+      const int gy = y0 + hy - 1, gx = x0 + hx - 1;
+      const bool in = gy >= 0 && gy < a.H && gx >= 0 && gx < a.W;
+#pragma unroll
+      for (int j4 = 0; j4 < C::CPT / 4; ++j4) {
+        float4 o;
+        const float* bb = sB1 + cg * C::CPT + j4 * 4;
+        o.x = in ? acc[i][j4 * 4 + 0] + bb[0] : 0.f;
+        o.y = in ? acc[i][j4 * 4 + 1] + bb[1] : 0.f;
+        o.z = in ? acc[i][j4 * 4 + 2] + bb[2] : 0.f;
+        o.w = in ? acc[i][j4 * 4 + 3] + bb[3] : 0.f;
+        *reinterpret_cast<float4*>(sY + pix * COUT + cg * C::CPT + j4 * 4) = o;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- stage 3: depthwise 3x3 from shared memory, store z, statistics
+  {
+    const int q = tid % C::NQ;
+    const int x = (tid / C::NQ) % TW;
+    const int rg = tid / (C::NQ * TW);
+    const int r0 = rg * C::RPT;
+    float4 w[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) w[k] = *reinterpret_cast<const float4*>(sW2 + k * COUT + q * 4);
+    const float4 bias = *reinterpret_cast<const float4*>(sB2 + q * 4);
+    float4 ra[3], rb[3], rc[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      ra[d] = *reinterpret_cast<const float4*>(sY + ((r0 + 0) * HW + x + d) * COUT + q * 4);
+      rb[d] = *reinterpret_cast<const float4*>(sY + ((r0 + 1) * HW + x + d) * COUT + q * 4);
+    }
+    float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+    const int gx = x0 + x;
+#pragma unroll
+    for (int i = 0; i < C::RPT; ++i) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d)
+        rc[d] = *reinterpret_cast<const float4*>(sY + ((r0 + i + 2) * HW + x + d) * COUT + q * 4);
+      float4 o = bias;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        fma4(o, w[d], ra[d]);
+        fma4(o, w[3 + d], rb[d]);
+        fma4(o, w[6 + d], rc[d]);
+      }
+      const int gy = y0 + r0 + i;
+      if (gy < a.H && gx < a.W) {
+        float* dst = a.zout + (long long)b * a.out_batch_stride + ((long long)gy * a.W + gx) * COUT + q * 4;
+        *reinterpret_cast<float4*>(dst) = o;
+        s1 = add4(s1, o);
+        s2.x = fmaf(o.x, o.x, s2.x); s2.y = fmaf(o.y, o.y, s2.y);
+        s2.z = fmaf(o.z, o.z, s2.z); s2.w = fmaf(o.w, o.w, s2.w);
+      }
+#pragma unroll
+      for (int d = 0; d < 3; ++d) { ra[d] = rb[d]; rb[d] = rc[d]; }
+    }
+    if (a.osum != nullptr) {
+      *reinterpret_cast<float4*>(sRed + tid * 8) = s1;
+      *reinterpret_cast<float4*>(sRed + tid * 8 + 4) = s2;
+    }
+  }
+  if (a.osum != nullptr) {
+    __syncthreads();
+    if (tid < 2 * COUT) {
+      const int c = tid % COUT, which = tid / COUT;
+      const int q = c / 4, lane = c % 4;
+      double s = 0.0;
+      for (int th = q; th < NT; th += C::NQ) s += (double)sRed[th * 8 + which * 4 + lane];
+      atomicAdd((which == 0 ? a.osum : a.osumsq) + c, s);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------- stem
+constexpr int ST_TH = 8, ST_TW = 32;
+constexpr int ST_IH = 2 * ST_TH + 1, ST_IW = 2 * ST_TW + 1;   // 17 x 65 input patch
+constexpr int ST_IWP = ST_IW + 2;                             // row stride 67 (odd: fewer conflicts)
+
+__global__ void __launch_bounds__(256) stem_fwd_kernel(const StemArgs a) {
+  __shared__ float sIn[3][ST_IH][ST_IWP];
+  __shared__ __align__(16) float sW[27][16];
+  __shared__ float sB[16];
+  __shared__ float sRed[8][32];
+  const int tid = threadIdx.x;
+  const int Ho = a.Hin / 2, Wo = a.Win / 2;
+  const int tiles_x = (Wo + ST_TW - 1) / ST_TW, tiles_y = (Ho + ST_TH - 1) / ST_TH;
+  int t = blockIdx.x;
+  const int tx = t % tiles_x; t /= tiles_x;
+  const int ty = t % tiles_y;
+  const int b = t / tiles_y;
+  const int ox0 = tx * ST_TW, oy0 = ty * ST_TH;
+  const int ix0 = 2 * ox0 - 1, iy0 = 2 * oy0 - 1;
+
+  for (int i = tid; i < 27 * 16; i += 256) {
+    int k = i / 16, co = i % 16;
+    sW[k][co] = __ldg(a.w + co * 27 + k);
+  }
+  if (tid < 16) sB[tid] = __ldg(a.b + tid);
+  for (int i = tid; i < 3 * ST_IH * ST_IW; i += 256) {
+    int c = i / (ST_IH * ST_IW);
+    int r = (i / ST_IW) % ST_IH;
+    int x = i % ST_IW;
+    int gy = iy0 + r, gx = ix0 + x;
+    float v = 0.f;
+    if (gy >= 0 && gy < a.Hin && gx >= 0 && gx < a.Win)
+      v = __ldg(a.img + (((long long)b * 3 + c) * a.Hin + gy) * a.Win + gx);
+    sIn[c][r][x] = v;
+  }
+  __syncthreads();
+
+  const int lx = tid % ST_TW, ly = tid / ST_TW;
+  float acc[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = sB[j];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const float v = sIn[c][2 * ly + ky][2 * lx + kx];
+        const int k = c * 9 + ky * 3 + kx;
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 w = *reinterpret_cast<const float4*>(&sW[k][j4 * 4]);
+          acc[j4 * 4 + 0] = fmaf(v, w.x, acc[j4 * 4 + 0]);
+          acc[j4 * 4 + 1] = fmaf(v, w.y, acc[j4 * 4 + 1]);
+          acc[j4 * 4 + 2] = fmaf(v, w.z, acc[j4 * 4 + 2]);
+          acc[j4 * 4 + 3] = fmaf(v, w.w, acc[j4 * 4 + 3]);
+        }
+      }
+  const int oy = oy0 + ly, ox = ox0 + lx;
+  const bool valid = oy < Ho && ox < Wo;
+  if (valid) {
+    float* dst = a.zout + (((long long)b * Ho + oy) * Wo + ox) * 16;
+#pragma unroll
+    for (int j4 = 0; j4 < 4; ++j4)
+      *reinterpret_cast<float4*>(dst + j4 * 4) =
+          make_float4(acc[j4 * 4], acc[j4 * 4 + 1], acc[j4 * 4 + 2], acc[j4 * 4 + 3]);
+  }
+  if (a.osum != nullptr) {
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float s1 = valid ? acc[j] : 0.f;
+      float s2 = valid ? acc[j] * acc[j] : 0.f;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      }
+      if (lane == 0) { sRed[warp][j] = s1; sRed[warp][16 + j] = s2; }
+    }
+    __syncthreads();
+    if (tid < 32) {
+      double s = 0.0;
+      for (int w = 0; w < 8; ++w) s += (double)sRed[w][tid];
+      atomicAdd((tid < 16 ? a.osum : a.osumsq) + (tid & 15), s);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------- BN running stats
+__global__ void bn_update_running_kernel(const BnFinalizeArgs a, const double* sum,
+                                         const double* sumsq, float* rmean, float* rvar,
+                                         float momentum) {
+  const int i = blockIdx.x;
+  const int c = threadIdx.x;
+  if (i >= a.n || c >= a.C[i]) return;
+  const long long o = a.ch_off[i] + c;
+  const double n = a.count[i];
+  const double m = sum[o] / n;
+  double v = sumsq[o] / n - m * m;
+  if (v < 0.0) v = 0.0;
+  const double unbiased = n > 1.0 ? v * n / (n - 1.0) : v;
+  rmean[o] = (1.f - momentum) * rmean[o] + momentum * (float)m;
+  rvar[o] = (1.f - momentum) * rvar[o] + momentum * (float)unbiased;
+}
+
+// ------------------------------------------------------------------------------- read activation
+__global__ void read_activation_kernel(const float* z, const BnRef bn, int has_bn, int B, int H,
+                                       int W, int C, long long batch_stride, float* out) {
+  const long long total = (long long)B * C * H * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int x = i % W;
+    const int y = (i / W) % H;
+    const int c = (i / ((long long)W * H)) % C;
+    const int b = i / ((long long)W * H * C);
+    float v = z[(long long)b * batch_stride + ((long long)y * W + x) * C + c];
+    if (has_bn) {
+      float sc, sh;
+      bn_coeffs(bn, c, sc, sh);
+      v = fmaxf(fmaf(v, sc, sh), 0.f);
+    }
+    out[i] = v;
+  }
+}
+
+__global__ void grid_priors_kernel(float* priors, int h0, int w0, int s0, int h1, int w1, int s1,
+                                   int h2, int w2, int s2) {
+  const int n0 = h0 * w0, n1 = h1 * w1, n2 = h2 * w2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n0 + n1 + n2) return;
+  int j = i, w = w0, s = s0;
+  if (i >= n0 + n1) { j = i - n0 - n1; w = w2; s = s2; }
+  else if (i >= n0) { j = i - n0; w = w1; s = s1; }
+  priors[i * 4 + 0] = (float)((j % w) * s);
+  priors[i * 4 + 1] = (float)((j / w) * s);
+  priors[i * 4 + 2] = (float)s;
+  priors[i * 4 + 3] = (float)s;
+}
+
+template <int CIN, int COUT, int MODE>
+cudaError_t launch_unit_fwd_t(const UnitFwdArgs& a, cudaStream_t s) {
+  using C = FwdCfg<CIN, COUT>;
+  const size_t smem = sizeof(float) * C::SMEM_FLOATS;
+  auto kern = unit_fwd_kernel<CIN, COUT, MODE>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const int tiles = ((a.W + TW - 1) / TW) * ((a.H + TH - 1) / TH);
+  kern<<<tiles * a.B, NT, smem, s>>>(a);
+  return cudaGetLastError();
+}
+
+template <int CIN, int COUT>
+cudaError_t launch_unit_fwd_m(int mode, const UnitFwdArgs& a, cudaStream_t s) {
+  switch (mode) {
+    case 0: return launch_unit_fwd_t<CIN, COUT, 0>(a, s);
+    case 1: return launch_unit_fwd_t<CIN, COUT, 1>(a, s);
+    case 2: return launch_unit_fwd_t<CIN, COUT, 2>(a, s);
+  }
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace
+
+int unit_fwd_supported(int cin, int cout) {
+  return (cin == 16 && (cout == 16 || cout == 32 || cout == 64)) ||
+         (cin == 32 && (cout == 32 || cout == 64)) || (cin == 64 && (cout == 64 || cout == 16));
+}
+
+cudaError_t launch_unit_fwd(int cin, int cout, int mode, const UnitFwdArgs& a, cudaStream_t s) {
+  if (cin == 16 && cout == 16) return launch_unit_fwd_m<16, 16>(mode, a, s);
+  if (cin == 16 && cout == 32) return launch_unit_fwd_m<16, 32>(mode, a, s);
+  if (cin == 16 && cout == 64) return launch_unit_fwd_m<16, 64>(mode, a, s);
+  if (cin == 32 && cout == 32) return launch_unit_fwd_m<32, 32>(mode, a, s);
+  if (cin == 32 && cout == 64) return launch_unit_fwd_m<32, 64>(mode, a, s);
+  if (cin == 64 && cout == 64) return launch_unit_fwd_m<64, 64>(mode, a, s);
+  if (cin == 64 && cout == 16) return launch_unit_fwd_m<64, 16>(mode, a, s);
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_stem_fwd(const StemArgs& a, cudaStream_t s) {
+  const int Ho = a.Hin / 2, Wo = a.Win / 2;
+  const int tiles = ((Wo + ST_TW - 1) / ST_TW) * ((Ho + ST_TH - 1) / ST_TH);
+  stem_fwd_kernel<<<tiles * a.B, 256, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bn_update_running(const BnFinalizeArgs& a, const double* sum,
+                                     const double* sumsq, float* rmean, float* rvar,
+                                     float momentum, cudaStream_t s) {
+  bn_update_running_kernel<<<a.n, 64, 0, s>>>(a, sum, sumsq, rmean, rvar, momentum);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_read_activation(const float* z, const BnRef& bn, int has_bn, int B, int H,
+                                   int W, int C, long long batch_stride, float* out_nchw,
+                                   cudaStream_t s) {
+  const long long total = (long long)B * C * H * W;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  read_activation_kernel<<<blocks, 256, 0, s>>>(z, bn, has_bn, B, H, W, C, batch_stride, out_nchw);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_grid_priors(float* priors, const int* lh, const int* lw, const int* strides,
+                               cudaStream_t s) {
+  const int n = lh[0] * lw[0] + lh[1] * lw[1] + lh[2] * lw[2];
+  grid_priors_kernel<<<(n + 255) / 256, 256, 0, s>>>(priors, lh[0], lw[0], strides[0], lh[1], lw[1],
+                                                     strides[1], lh[2], lw[2], strides[2]);
+  return cudaGetLastError();
+}
+
+}  // namespace yunet
