@@ -188,6 +188,18 @@ int yunet_read_activation(yunet_ctx* ctx, int unit_index, const float* params,
                           const float* bn_running, int B, int H, int W, int train, const void* ws,
                           float* out_nchw, void* stream);
 
+/* ---- measurement helpers (bench.py) ---------------------------------------------------------------
+ * yunet_launch_count: kernels launched through this ctx so far.  yunet_profile_begin/end bracket
+ * a region in which every kernel launch of the entry points above is timed with its own pair of
+ * CUDA events on the launching stream; yunet_profile_end synchronises on them and returns the
+ * number of records, yunet_profile_get returns name ("fwd:<unit>", "bwd:<unit>", ...), duration
+ * and the algorithmic bytes of record i. */
+long long yunet_launch_count(const yunet_ctx* ctx);
+int yunet_profile_begin(yunet_ctx* ctx);
+int yunet_profile_end(yunet_ctx* ctx);
+int yunet_profile_get(const yunet_ctx* ctx, int i, char* name, int name_cap, float* ms,
+                      double* algorithmic_bytes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -79,6 +79,10 @@ def _load():
         'yunet_unit_count': (ci, [vp]),
         'yunet_unit_get': (ci, [vp, ci, P(UnitDesc)]),
         'yunet_read_activation': (ci, [vp, ci, vp, vp, ci, ci, ci, ci, vp, vp, vp]),
+        'yunet_launch_count': (ll, [vp]),
+        'yunet_profile_begin': (ci, [vp]),
+        'yunet_profile_end': (ci, [vp]),
+        'yunet_profile_get': (ci, [vp, ci, C.c_char_p, ci, P(cf), P(C.c_double)]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)      # AttributeError here == header/library mismatch
@@ -136,6 +140,7 @@ class Ctx:
             msg = lib.yunet_last_error(self._h) if self._h else b'allocation failed'
             if self._h:
                 lib.yunet_ctx_destroy(self._h)
+            self._h = None
             raise YuNetError(f'yunet_ctx_create failed ({code}): {msg.decode()}')
         self.num_params = lib.yunet_num_params(self._h)
         self.num_bn_channels = lib.yunet_num_bn_channels(self._h)

@@ -6,17 +6,28 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "kernels.h"
 #include "plan.h"
 
 using namespace yunet;
 
+struct ProfEvent {
+  std::string name;
+  cudaEvent_t start = nullptr, stop = nullptr;
+  double bytes = 0.0;   // algorithmic bytes of the launch, 0 if not a streaming kernel
+};
+
 struct yunet_ctx {
   Plan plan;
   std::string err;
   int num_sms = 148;
   bool sms_known = false;
+  long long launches = 0;       // kernels launched by this ctx (bench.py's gpu_launches)
+  bool profiling = false;
+  std::vector<ProfEvent> prof;
+  std::vector<float> prof_ms;
 };
 
 namespace {
@@ -129,6 +140,27 @@ LevelGeom make_geom(const Plan& p, int H, int W) {
   return g;
 }
 
+// RAII: counts the launch and, when profiling, brackets it with CUDA events on the stream.
+struct Scope {
+  yunet_ctx* c;
+  cudaStream_t s;
+  int idx = -1;
+  Scope(yunet_ctx* c_, cudaStream_t s_, const std::string& name, double bytes = 0.0) : c(c_), s(s_) {
+    c->launches++;
+    if (!c->profiling) return;
+    ProfEvent e;
+    e.name = name;
+    e.bytes = bytes;
+    if (cudaEventCreate(&e.start) != cudaSuccess || cudaEventCreate(&e.stop) != cudaSuccess) return;
+    cudaEventRecord(e.start, s);
+    c->prof.push_back(e);
+    idx = (int)c->prof.size() - 1;
+  }
+  ~Scope() {
+    if (idx >= 0) cudaEventRecord(c->prof[idx].stop, s);
+  }
+};
+
 void copy_name(char* dst, int cap, const std::string& s) {
   if (!dst || cap <= 0) return;
   snprintf(dst, (size_t)cap, "%s", s.c_str());
@@ -159,7 +191,11 @@ int yunet_ctx_create(const yunet_arch_cfg* cfg, yunet_ctx** out) {
   return 0;
 }
 
-void yunet_ctx_destroy(yunet_ctx* ctx) { delete ctx; }
+void yunet_ctx_destroy(yunet_ctx* ctx) {
+  if (!ctx) return;
+  for (ProfEvent& e : ctx->prof) { cudaEventDestroy(e.start); cudaEventDestroy(e.stop); }
+  delete ctx;
+}
 
 const char* yunet_last_error(const yunet_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
 
@@ -259,7 +295,10 @@ int yunet_forward(yunet_ctx* ctx, const float* img, const float* params, float* 
     a.osum = train ? v.stat(0) + bn.ch_off : nullptr;
     a.osumsq = train ? v.stat(1) + bn.ch_off : nullptr;
     a.B = B; a.Hin = H; a.Win = W;
-    e = launch_stem_fwd(a, s);
+    {
+      Scope sc(ctx, s, "fwd:stem", 4.0 * B * (3.0 * H * W + 16.0 * (H / 2) * (W / 2)));
+      e = launch_stem_fwd(a, s);
+    }
     if (e != cudaSuccess) return cuda_fail(ctx, e, "forward: stem");
   }
   for (const UnitDesc& u : p.units) {
@@ -283,11 +322,18 @@ int yunet_forward(yunet_ctx* ctx, const float* img, const float* params, float* 
       a.osum = v.stat(0) + bn.ch_off;
       a.osumsq = v.stat(1) + bn.ch_off;
     }
-    e = launch_unit_fwd(u.cin, u.cout, u.mode, a, s);
+    {
+      const double hw = (double)a.H * a.W;
+      double bytes = 4.0 * B * (u.cin * hw * (u.mode == LOAD_POOL ? 4.0 : 1.0) + u.cout * hw);
+      if (u.mode == LOAD_UPADD) bytes += 4.0 * B * u.cin * hw / 4.0;
+      Scope sc(ctx, s, "fwd:" + u.name, bytes);
+      e = launch_unit_fwd(u.cin, u.cout, u.mode, a, s);
+    }
     if (e != cudaSuccess) return fail(ctx, (int)e, "forward: unit %s: %s", u.name.c_str(), cudaGetErrorString(e));
   }
   if (train && bn_running) {
     BnFinalizeArgs fa = make_bn_args(p, B, H, W);
+    Scope sc(ctx, s, "fwd:bn_running");
     e = launch_bn_update_running(fa, v.stat(0), v.stat(1), bn_running, bn_running + p.num_bn_ch,
                                  momentum, s);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "forward: running statistics");
@@ -329,6 +375,7 @@ int yunet_simota_assign(yunet_ctx* ctx, const yunet_loss_cfg* lc, const float* p
   LevelGeom g = make_geom(ctx->plan, H, W);
   const size_t need = simota_workspace_bytes(B, g.P);
   if (need > 0 && (!ws || ws_bytes < need)) return fail(ctx, -3, "simota_assign: workspace too small");
+  Scope sc(ctx, (cudaStream_t)stream, "simota_assign");
   return cuda_fail(ctx, launch_simota_assign(to_dev(lc), g, preds, gt, gt_offsets, B, assigned_gt,
                                              matched_iou, counters, ws, (cudaStream_t)stream),
                    "simota_assign");
@@ -345,6 +392,7 @@ int yunet_loss_grad(yunet_ctx* ctx, const yunet_loss_cfg* lc, const float* preds
   LevelGeom g = make_geom(ctx->plan, H, W);
   float sc[4] = {1.f, 1.f, 1.f, 1.f};
   if (loss_scale) for (int i = 0; i < 4; ++i) sc[i] = loss_scale[i];
+  Scope scope(ctx, (cudaStream_t)stream, "loss_grad");
   return cuda_fail(ctx, launch_loss_grad(to_dev(lc), g, preds, gt, gt_offsets, assigned_gt,
                                          matched_iou, counters, num_total_samples, sc[0], sc[1],
                                          sc[2], sc[3], B, losses, d_preds, (cudaStream_t)stream),
@@ -407,7 +455,14 @@ int yunet_backward(yunet_ctx* ctx, const float* img, const float* params, const 
     }
     a.gw1 = grad_bucket + u.w1; a.gb1 = grad_bucket + u.b1;
     a.gw2 = grad_bucket + u.w2; a.gb2 = grad_bucket + u.b2;
-    e = launch_unit_bwd(u.cin, u.cout, u.mode, a, ctx->num_sms, s);
+    {
+      const double hw = (double)a.H * a.W;
+      double bytes = 4.0 * B * (2.0 * u.cin * hw * (u.mode == LOAD_POOL ? 4.0 : 1.0) +
+                                (u.has_bn ? 2.0 : 1.0) * u.cout * hw);
+      if (u.mode == LOAD_UPADD) bytes += 4.0 * B * 2.0 * u.cin * hw / 4.0;
+      Scope sc(ctx, s, "bwd:" + u.name, bytes);
+      e = launch_unit_bwd(u.cin, u.cout, u.mode, a, ctx->num_sms, s);
+    }
     if (e != cudaSuccess) return fail(ctx, (int)e, "backward: unit %s: %s", u.name.c_str(), cudaGetErrorString(e));
   }
   {
@@ -418,11 +473,15 @@ int yunet_backward(yunet_ctx* ctx, const float* img, const float* params, const 
     a.dsum = v.stat(2) + bn.ch_off; a.dsumzh = v.stat(3) + bn.ch_off;
     a.gw = grad_bucket + p.stem_w; a.gb = grad_bucket + p.stem_b;
     a.B = B; a.Hin = H; a.Win = W;
+    Scope sc(ctx, s, "bwd:stem", 4.0 * B * (3.0 * H * W + 2.0 * 16.0 * (H / 2) * (W / 2)));
     e = launch_stem_bwd(a, ctx->num_sms, s);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "backward: stem");
   }
   BnFinalizeArgs fa = make_bn_args(p, B, H, W);
-  e = launch_bn_param_grads(fa, v.stat(2), v.stat(3), grad_bucket, s);
+  {
+    Scope sc(ctx, s, "bwd:bn_param_grads");
+    e = launch_bn_param_grads(fa, v.stat(2), v.stat(3), grad_bucket, s);
+  }
   return cuda_fail(ctx, e, "backward: bn parameter grads");
 }
 
@@ -430,6 +489,7 @@ int yunet_sgd_step(yunet_ctx* ctx, float* params, const float* grad_bucket, floa
                    long long n, float lr, float momentum, float weight_decay, float grad_scale,
                    void* stream) {
   if (!params || !grad_bucket || !momentum_buf || n <= 0) return fail(ctx, -1, "sgd_step: bad arguments");
+  Scope sc(ctx, (cudaStream_t)stream, "sgd_step");
   return cuda_fail(ctx, launch_sgd(params, grad_bucket, momentum_buf, n, lr, momentum, weight_decay,
                                    grad_scale, (cudaStream_t)stream), "sgd_step");
 }
@@ -446,9 +506,42 @@ int yunet_decode_nms(yunet_ctx* ctx, const float* preds, int B, int H, int W, fl
   if (!shape_ok(ctx, B, H, W) || max_det <= 0) return fail(ctx, -2, "decode_nms: bad shape");
   LevelGeom g = make_geom(ctx->plan, H, W);
   if (ws_bytes < nms_workspace_bytes(B, g.P)) return fail(ctx, -3, "decode_nms: workspace too small");
+  Scope sc(ctx, (cudaStream_t)stream, "decode_nms");
   return cuda_fail(ctx, launch_decode_nms(g, preds, B, score_thr, iou_thr, scale_factors, max_det,
                                           dets, det_kps, det_count, ws, (cudaStream_t)stream),
                    "decode_nms");
+}
+
+long long yunet_launch_count(const yunet_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int yunet_profile_begin(yunet_ctx* ctx) {
+  if (!ctx) return -1;
+  for (ProfEvent& e : ctx->prof) { cudaEventDestroy(e.start); cudaEventDestroy(e.stop); }
+  ctx->prof.clear();
+  ctx->prof_ms.clear();
+  ctx->profiling = true;
+  return 0;
+}
+
+int yunet_profile_end(yunet_ctx* ctx) {
+  if (!ctx) return -1;
+  ctx->profiling = false;
+  ctx->prof_ms.assign(ctx->prof.size(), 0.f);
+  for (size_t i = 0; i < ctx->prof.size(); ++i) {
+    cudaError_t e = cudaEventSynchronize(ctx->prof[i].stop);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "profile_end");
+    cudaEventElapsedTime(&ctx->prof_ms[i], ctx->prof[i].start, ctx->prof[i].stop);
+  }
+  return (int)ctx->prof.size();
+}
+
+int yunet_profile_get(const yunet_ctx* ctx, int i, char* name, int name_cap, float* ms,
+                      double* algorithmic_bytes) {
+  if (!ctx || i < 0 || i >= (int)ctx->prof_ms.size()) return -1;
+  copy_name(name, name_cap, ctx->prof[i].name);
+  if (ms) *ms = ctx->prof_ms[i];
+  if (algorithmic_bytes) *algorithmic_bytes = ctx->prof[i].bytes;
+  return 0;
 }
 
 }  // extern "C"

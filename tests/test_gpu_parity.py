@@ -1,0 +1,337 @@
+"""GPU parity tests (run on the B200 box: ``pytest -m gpu``).  Every call goes through the C ABI of
+libyunet_b200.so (via the ctypes host mirror); the checker is the CPU oracle and the committed
+golden fixtures generated from the unmodified reference.
+
+Tolerances: 1e-3 relative fp32 on values (``BASELINE.json: north_star``; measured errors are
+~1e-5), exact on prior / assignment indices (modulo cost ties where ``torch.topk`` leaves the
+order unspecified — see ``_tie_equivalent``)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+from oracle import yunet_oracle as orc  # noqa: E402
+from libfacedetection.train_b200 import synthetic  # noqa: E402
+
+TOL = 1e-3
+
+
+def _engine(arch, pretrained=True):
+    from libfacedetection.train_b200 import YuNetEngine
+    eng = YuNetEngine(arch)
+    if pretrained:
+        d = np.load(os.path.join(GOLDEN, f'weights_{arch}.npz'))
+        eng.load_state_dict({k: torch.from_numpy(d[k]) for k in d.files})
+    else:
+        eng.init_weights(0)
+    return eng
+
+
+def _weights(arch):
+    d = np.load(os.path.join(GOLDEN, f'weights_{arch}.npz'))
+    return orc.split_state_dict({k: torch.from_numpy(d[k]) for k in d.files})
+
+
+def _rel(a, b):
+    a = torch.as_tensor(a).detach().double().cpu()
+    b = torch.as_tensor(b).detach().double().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def _gt_to_device(gb, gk, device):
+    gt, offs = synthetic.pack_gt_csr(gb, gk)
+    return torch.from_numpy(gt).to(device), torch.from_numpy(offs).to(device)
+
+
+# --------------------------------------------------------------------------------- forward
+@pytest.mark.parametrize('arch,size', [('yunet_n', 320), ('yunet_s', 320), ('yunet_n', 640)])
+def test_forward_eval_matches_reference_golden(arch, size):
+    g = np.load(os.path.join(GOLDEN, f'forward_{arch}_{size}.npz'))
+    eng = _engine(arch)
+    torch.manual_seed(0)
+    img = torch.rand(1, 3, size, size) * 255
+    preds = eng.forward(img.cuda(), train=False)
+    err = _rel(preds, g['preds'])
+    print(f'forward {arch} {size}: rel err vs reference {err:.3e}')
+    assert err < TOL
+
+
+@pytest.mark.parametrize('arch', ['yunet_n', 'yunet_s'])
+@pytest.mark.parametrize('train', [False, True])
+def test_every_unit_matches_oracle(arch, train):
+    """Per fused unit: the activation the reference module returns (post BN+ReLU), eval and
+    train-mode BatchNorm, ragged sizes (96x160 -> tiles partially filled at every level)."""
+    eng = _engine(arch)
+    B, H, W = 3, 96, 160
+    rng = np.random.default_rng(5)
+    img = torch.from_numpy(rng.random((B, 3, H, W), dtype=np.float32) * 255)
+    P, Bf = _weights(arch)
+    captured = {}
+    orig = orc.conv_dp_unit
+
+    def spy(x, P_, Bf_, prefix, with_bn_relu, training):
+        out = orig(x, P_, Bf_, prefix, with_bn_relu, training)
+        captured[prefix] = out
+        return out
+
+    orc.conv_dp_unit = spy
+    try:
+        with torch.no_grad():
+            outs = orc.model_forward(img, P, Bf, arch, training=train)
+    finally:
+        orc.conv_dp_unit = orig
+    preds = eng.forward(img.cuda(), train=train)
+    worst = 0.0
+    for i, u in enumerate(eng.ctx.units()):
+        name = u.name.decode()
+        if u.pred_level >= 0:
+            continue
+        mine = eng.read_activation(i, B, H, W, train=train)
+        err = _rel(mine, captured[name])
+        worst = max(worst, err)
+        assert err < TOL, f'unit {i} {name}: rel err {err:.3e}'
+    f = orc.flatten_preds(*outs)
+    ref = torch.cat([f[0], f[1], f[2].unsqueeze(-1), f[3]], -1)
+    err = _rel(preds, ref)
+    print(f'{arch} train={train}: worst unit err {worst:.3e}, preds err {err:.3e}')
+    assert err < TOL
+    if train:
+        # running statistics updated like torch BatchNorm2d (momentum 0.1, unbiased var)
+        sd = eng.state_dict()
+        for k, v in Bf.items():
+            if v.dtype.is_floating_point:
+                assert _rel(sd[k], v) < TOL, k
+
+
+def test_priors_index_exact():
+    eng = _engine('yunet_n', pretrained=False)
+    for size in (320, 640):
+        ref = torch.cat(orc.grid_priors([(size // s, size // s) for s in (8, 16, 32)], (8, 16, 32)))
+        assert torch.equal(eng.grid_priors(size, size).cpu(), ref)
+
+
+# --------------------------------------------------------------------------------- SimOTA + loss
+def _tie_equivalent(assigned_mine, assigned_ref, dbg):
+    """Same assignment up to a swap between candidates whose cost for that gt is identical in fp32
+    (the additive 1e5 quantises costs; torch.topk's tie order is unspecified)."""
+    cost, valid = dbg['cost'], dbg['valid']
+    vidx = torch.nonzero(valid).squeeze(-1)
+    pos_of = {int(p): i for i, p in enumerate(vidx)}
+    G = cost.shape[1]
+    for g in range(G):
+        mine = sorted(pos_of[int(p)] for p in torch.nonzero(assigned_mine == g + 1).squeeze(-1)
+                      if int(p) in pos_of)
+        ref = sorted(pos_of[int(p)] for p in torch.nonzero(assigned_ref == g + 1).squeeze(-1))
+        if len(mine) != len(ref):
+            return False
+        cm = sorted(float(cost[i, g]) for i in mine)
+        cr = sorted(float(cost[i, g]) for i in ref)
+        if cm != cr:
+            return False
+    return True
+
+
+def _check_assignment(eng, preds, gb, gl, gk, H, W):
+    """Assignment of the CUDA kernel vs the oracle run on the SAME predictions."""
+    B = preds.shape[0]
+    gt, offs = _gt_to_device(gb, gk, preds.device)
+    assigned, miou, counters = eng.assign(preds, gt, offs, H, W)
+    assigned = assigned.cpu().long()
+    miou = miou.cpu()
+    pc = preds.cpu()
+    priors = torch.cat(orc.grid_priors([(H // s, W // s) for s in (8, 16, 32)], (8, 16, 32)))
+    exact = tie = 0
+    npos = 0
+    wsum = 0.0
+    for b in range(B):
+        cls, bbox, obj = pc[b, :, 0:1], pc[b, :, 1:5], pc[b, :, 5]
+        boxes = orc.bbox_decode(priors, bbox)
+        off_pri = torch.cat([priors[:, :2] + priors[:, 2:] * 0.5, priors[:, 2:]], -1)
+        ref_a, ref_ov, dbg = orc.simota_assign(cls.sigmoid() * obj.unsqueeze(1).sigmoid(), off_pri,
+                                               boxes, torch.from_numpy(gb[b]),
+                                               torch.from_numpy(gl[b]), return_debug=True)
+        if torch.equal(assigned[b], ref_a):
+            exact += 1
+            pos = ref_a > 0
+            np.testing.assert_allclose(miou[b][pos].numpy(), ref_ov[pos].numpy(), rtol=1e-5, atol=1e-6)
+        else:
+            assert _tie_equivalent(assigned[b], ref_a, dbg), f'image {b}: assignment differs beyond cost ties'
+            tie += 1
+        npos += int((assigned[b] > 0).sum())
+        kw = torch.from_numpy(gk[b])[:, :, 2].mean(1)
+        wsum += float(kw[assigned[b][assigned[b] > 0] - 1].sum())
+    c = counters.cpu()
+    assert int(c[0]) == npos
+    assert abs(float(c[1]) - wsum) < 1e-3 * max(1.0, wsum)
+    return exact, tie, (gt, offs, assigned, miou, counters)
+
+
+@pytest.mark.parametrize('arch,seed', [('yunet_n', 0), ('yunet_s', 1)])
+def test_train_step_matches_reference_golden(arch, seed):
+    """forward(train) -> SimOTA -> losses -> backward -> SGD on the golden 4-image batch."""
+    g = np.load(os.path.join(GOLDEN, f'train_{arch}_b4.npz'))
+    B, size = int(g['B']), int(g['size'])
+    eng = _engine(arch)
+    img = torch.from_numpy(synthetic.make_images(B, size, seed)).cuda()
+    gb, gl, gk = synthetic.make_gt(B, size, seed)
+    preds = eng.forward(img, train=True)
+    err = _rel(preds, g['preds'])
+    print(f'{arch}: train-mode preds rel err {err:.3e}')
+    assert err < TOL
+    exact, tie, (gt, offs, assigned, miou, counters) = _check_assignment(eng, preds, gb, gl, gk, size, size)
+    print(f'{arch}: assignment exact on {exact}/{B} images, tie-equivalent on {tie}')
+    same_as_golden = np.array_equal(assigned.numpy(), g['assigned_gt_inds'])
+    losses, d_preds = eng.loss_grad(preds, gt, offs, eng._bufs[('assigned', (B, preds.shape[1]), torch.int32)],
+                                    eng._bufs[('miou', (B, preds.shape[1]), torch.float32)], counters,
+                                    counters, size, size)
+    eng.backward(img, d_preds)
+    if not same_as_golden:
+        pytest.skip('assignment differs from the golden one only by cost ties; value parity is '
+                    'covered by test_loss_and_grads_match_oracle')
+    ref_l = g['losses']
+    mine_l = losses.cpu().numpy()
+    for i, k in enumerate(('loss_cls', 'loss_bbox', 'loss_obj', 'loss_kps')):
+        assert abs(mine_l[i] - ref_l[i]) <= TOL * max(1.0, abs(ref_l[i])), (k, mine_l[i], ref_l[i])
+    grads = eng.param_views(eng.grads)
+    gmax = max(float(np.abs(g['grad/' + k]).max()) for k in grads)
+    worst = 0.0
+    for k, v in grads.items():
+        ref = torch.from_numpy(g['grad/' + k])
+        scale = float(ref.abs().max())
+        err = float((v.cpu() - ref).abs().max())
+        # biases that feed a train-mode BatchNorm have an exactly-zero true gradient; the reference
+        # value is rounding residue, so compare on the scale of the whole gradient
+        atol = 1e-5 * gmax
+        assert err <= TOL * scale + atol, f'{k}: err {err:.3e} scale {scale:.3e}'
+        worst = max(worst, err / (scale + atol))
+    print(f'{arch}: worst normalised grad err {worst:.3e}')
+    eng.sgd_step(0.01, 0.9, 0.0005, 1.0)
+    sd = eng.state_dict()
+    for k in grads:
+        assert _rel(sd[k], g['after/' + k]) < TOL, k
+    for k in sd:
+        if 'running_' in k:
+            assert _rel(sd[k], g['after/' + k]) < TOL, k
+
+
+@pytest.mark.parametrize('arch', ['yunet_n', 'yunet_s'])
+def test_loss_and_grads_match_oracle(arch):
+    """16 images, crowded ground truth; the oracle is forced onto the kernel's assignment so value
+    parity is checked independently of tie-breaking."""
+    B, size, seed = 16, 320, 11
+    eng = _engine(arch)
+    img_np = synthetic.make_images(B, size, seed)
+    gb, gl, gk = synthetic.make_gt(B, size, seed)
+    img = torch.from_numpy(img_np).cuda()
+    preds = eng.forward(img, train=True)
+    exact, tie, (gt, offs, assigned, miou, counters) = _check_assignment(eng, preds, gb, gl, gk, size, size)
+    print(f'{arch}: assignment exact {exact}/{B}, tie-equivalent {tie}')
+    losses, d_preds = eng.loss_grad(preds, gt, offs, eng._bufs[('assigned', (B, preds.shape[1]), torch.int32)],
+                                    eng._bufs[('miou', (B, preds.shape[1]), torch.float32)], counters,
+                                    counters, size, size)
+    eng.backward(img, d_preds)
+    # oracle with the kernel's assignment injected
+    P, Bf = _weights(arch)
+    Pg = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    outs = orc.model_forward(torch.from_numpy(img_np), Pg, Bf, arch, training=True)
+    orig = orc.simota_assign
+    it = iter(range(B))
+
+    def forced(*a, **k):
+        b = next(it)
+        ov = torch.where(assigned[b] > 0, miou[b], torch.full_like(miou[b], -1e5))
+        return assigned[b].clone(), ov
+
+    orc.simota_assign = forced
+    try:
+        ref_losses = orc.head_loss(*outs, [torch.from_numpy(x) for x in gb],
+                                   [torch.from_numpy(x) for x in gl],
+                                   [torch.from_numpy(x) for x in gk])
+    finally:
+        orc.simota_assign = orig
+    sum(ref_losses.values()).backward()
+    mine_l = losses.cpu().numpy()
+    for i, k in enumerate(('loss_cls', 'loss_bbox', 'loss_obj', 'loss_kps')):
+        r = float(ref_losses[k])
+        assert abs(mine_l[i] - r) <= TOL * max(1.0, abs(r)), (k, mine_l[i], r)
+    grads = eng.param_views(eng.grads)
+    gmax = max(float(Pg[k].grad.abs().max()) for k in grads)
+    worst = 0.0
+    for k, v in grads.items():
+        ref = Pg[k].grad
+        scale = float(ref.abs().max())
+        err = float((v.cpu() - ref).abs().max())
+        assert err <= TOL * scale + 1e-5 * gmax, f'{k}: err {err:.3e} scale {scale:.3e}'
+        worst = max(worst, err / (scale + 1e-5 * gmax))
+    print(f'{arch}: losses {mine_l}, worst normalised grad err {worst:.3e}')
+
+
+# --------------------------------------------------------------------------------- decode + NMS
+def test_nms_matches_reference_golden():
+    g = np.load(os.path.join(GOLDEN, 'nms_synth_640.npz'))
+    eng = _engine('yunet_n', pretrained=False)
+    preds = torch.from_numpy(g['preds']).cuda()
+    size = int(g['size'])
+    dets, counts, kps = eng.decode_nms(preds, size, size, 0.02, 0.45, with_kps=True)
+    counts = counts.cpu()
+    for b in range(preds.shape[0]):
+        ref = g[f'dets{b}']
+        n = int(counts[b])
+        assert n == ref.shape[0], (n, ref.shape)
+        mine = dets[b, :n].cpu().numpy()
+        # boxes/scores come from expf/sigmoid on the GPU: values to 1e-5, order identical
+        np.testing.assert_allclose(mine, ref, rtol=1e-4, atol=1e-3)
+    # idempotence property: NMS of the survivors keeps every one of them
+    n0 = int(counts[0])
+    d0 = dets[0, :n0].cpu()
+    keep = orc.nms_greedy(d0[:, :4], d0[:, 4], 0.45)
+    assert keep.numel() == n0
+    assert bool((d0[:-1, 4] >= d0[1:, 4]).all())
+
+
+def test_nms_on_real_forward_and_empty():
+    g = np.load(os.path.join(GOLDEN, 'forward_yunet_n_640.npz'))
+    eng = _engine('yunet_n')
+    torch.manual_seed(0)
+    img = (torch.rand(1, 3, 640, 640) * 255).cuda()
+    dets, counts, _ = eng.detect(img)
+    assert int(counts[0]) == g['dets'].shape[0]
+    if g['dets'].shape[0]:
+        np.testing.assert_allclose(dets[0, :int(counts[0])].cpu().numpy(), g['dets'], rtol=1e-3, atol=1e-2)
+    # all-background logits -> zero detections, no crash
+    preds = torch.full((2, 2100, 16), -20.0).cuda()
+    _, c, _ = eng.decode_nms(preds, 320, 320)
+    assert c.cpu().tolist() == [0, 0]
+
+
+# --------------------------------------------------------------------------------- full size
+def test_full_size_properties_bs256():
+    """BASELINE config 2 shape (bs=256, 320x320): size-independent properties."""
+    B, size = 256, 320
+    eng = _engine('yunet_n')
+    img = torch.from_numpy(synthetic.make_images(B, size, 7)).cuda()
+    gb, gl, gk = synthetic.make_gt(B, size, 7)
+    gt, offs = _gt_to_device(gb, gk, img.device)
+    # (a) eval forward of the batch == eval forward of a slice (images are independent)
+    full = eng.forward(img, train=False).clone()
+    part = eng.forward(img[100:108].contiguous(), train=False)
+    assert torch.equal(full[100:108], part)
+    # (b) a complete step is finite and the gradient is linear in d_preds
+    losses = eng.train_step(img, gt, offs, step=False).cpu()
+    assert bool(torch.isfinite(losses).all()) and float(losses.sum()) > 0
+    g1 = eng.grads.clone()
+    assert bool(torch.isfinite(g1).all())
+    d = eng._bufs[('d_preds', (B, 2100, 16), torch.float32)]
+    d.mul_(2.0)
+    eng.backward(img, d)
+    err = _rel(eng.grads, 2.0 * g1)
+    print(f'bs256: losses {losses.numpy()}, linearity err {err:.3e}')
+    assert err < 1e-4
+    # (c) every image has >= 1 positive (each gt gets dynamic_k >= 1)
+    a = eng._bufs[('assigned', (B, 2100), torch.int32)]
+    assert int(((a > 0).sum(1) == 0).sum()) == 0
