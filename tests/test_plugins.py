@@ -1,0 +1,79 @@
+"""CPU tests of the plugin surface: same names, ctor kwargs and state_dict keys as the reference
+(mmdet/models/{backbones/yunet_backbone,necks/tfpn,dense_heads/yunet_head}.py), so the shipped
+checkpoints load strict."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from libfacedetection.train_b200 import plugins
+
+CFG = {
+    'yunet_n': dict(stage=[[3, 16, 16], [16, 64], [64, 64], [64, 64], [64, 64], [64, 64]], shared=1),
+    'yunet_s': dict(stage=[[3, 16, 16], [16, 32], [32, 64], [64, 64], [64, 64], [64, 64]], shared=0),
+}
+
+
+def model_cfg(arch):
+    c = CFG[arch]
+    # the `model` dict of configs/yunet_{n,s}.py:104-145, verbatim structure
+    return dict(
+        type='YuNet',
+        backbone=dict(type='YuNetBackbone', stage_channels=c['stage'], downsample_idx=[0, 2, 3, 4],
+                      out_idx=[3, 4, 5]),
+        neck=dict(type='TFPN', in_channels=[64, 64, 64], out_idx=[0, 1, 2]),
+        bbox_head=dict(
+            type='YuNet_Head', num_classes=1, in_channels=64, shared_stacked_convs=c['shared'],
+            stacked_convs=0, feat_channels=64,
+            prior_generator=dict(type='MlvlPointGenerator', offset=0, strides=[8, 16, 32]),
+            loss_cls=dict(type='CrossEntropyLoss', use_sigmoid=True, reduction='sum', loss_weight=1.0),
+            loss_bbox=dict(type='EIoULoss', loss_weight=5.0, reduction='sum'),
+            use_kps=True, kps_num=5,
+            loss_kps=dict(type='SmoothL1Loss', beta=0.1111111111111111, loss_weight=0.1),
+            loss_obj=dict(type='CrossEntropyLoss', use_sigmoid=True, reduction='sum', loss_weight=1.0)),
+        train_cfg=dict(assigner=dict(type='SimOTAAssigner', center_radius=2.5)),
+        test_cfg=dict(nms_pre=-1, min_bbox_size=0, score_thr=0.02,
+                      nms=dict(type='nms', iou_threshold=0.45), max_per_img=-1))
+
+
+@pytest.mark.parametrize('arch', ['yunet_n', 'yunet_s'])
+def test_checkpoint_loads_strict(arch):
+    model = plugins.DETECTORS.build(model_cfg(arch))
+    d = np.load(os.path.join(GOLDEN, f'weights_{arch}.npz'))
+    sd = {k: torch.from_numpy(d[k]) for k in d.files}
+    mine = model.state_dict()
+    assert set(mine) == set(sd)
+    for k in sd:
+        assert tuple(mine[k].shape) == tuple(sd[k].shape), k
+    model.load_state_dict(sd, strict=True)
+    assert sum(p.numel() for p in model.parameters()) == {'yunet_n': 75856, 'yunet_s': 54608}[arch]
+    lc = model.bbox_head.loss_cfg
+    assert abs(lc.loss_bbox_weight - 5.0) < 1e-6 and abs(lc.smooth_l1_beta - 1 / 9) < 1e-6
+    assert abs(lc.center_radius - 2.5) < 1e-6 and lc.candidate_topk == 10
+
+
+def test_registries_hold_reference_names():
+    assert plugins.BACKBONES.get('YuNetBackbone') is plugins.YuNetBackbone
+    assert plugins.NECKS.get('TFPN') is plugins.TFPN
+    assert plugins.HEADS.get('YuNet_Head') is plugins.YuNet_Head
+    assert plugins.BBOX_ASSIGNERS.get('SimOTAAssigner') is plugins.SimOTAAssigner
+    a = plugins.BBOX_ASSIGNERS.build(dict(type='SimOTAAssigner', center_radius=2.5))
+    assert (a.center_radius, a.candidate_topk, a.iou_weight, a.cls_weight) == (2.5, 10, 3.0, 1.0)
+
+
+def test_reference_init_statistics():
+    torch.manual_seed(0)
+    m = plugins.DETECTORS.build(model_cfg('yunet_n'))
+    sd = m.state_dict()
+    assert float(sd['backbone.model2.conv1.conv1.bias'].mean()) == pytest.approx(0.02)
+    assert float(sd['backbone.model2.conv1.bn.weight'].mean()) == 1.0
+    w = sd['backbone.model2.conv1.conv1.weight']     # xavier normal: std = sqrt(2/(64+64))
+    assert abs(float(w.std()) - (2.0 / 128) ** 0.5) < 0.01
+
+
+def test_cpu_parameters_are_refused():
+    m = plugins.DETECTORS.build(model_cfg('yunet_s'))
+    with pytest.raises(RuntimeError):
+        m.feature_test(torch.zeros(1, 3, 64, 64))
