@@ -224,25 +224,22 @@ class YuNetEngine:
         """One full training iteration on this rank: forward (train-mode BN) -> SimOTA ->
         [all-reduce num_pos] -> losses + d_preds -> backward -> [all-reduce gradient bucket] ->
         fused SGD.  Returns the device tensor of the four losses [cls, bbox, obj, kps]."""
-        import torch.distributed as dist
+        from . import dist_utils
         B, _, H, W = img.shape
-        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         preds = self.forward(img, train=True, preds=self._buf('preds', (B, self.ctx.num_priors(H, W), 16), torch.float32))
         assigned, miou, counters = self.assign(preds, gt, gt_offsets, H, W)
         num_total = counters
-        if world > 1:
-            # reduce_mean(num_pos): dist_utils.py:68-74 (div by world, then all-reduce sum)
+        if dist_utils.world_size() > 1:
+            # reduce_mean(num_pos) sits between assignment and loss scaling (yunet_head.py:493-497)
             num_total = self._buf('num_total', (1,), torch.float32)
             num_total.copy_(counters[:1])
-            num_total.div_(world)
-            dist.all_reduce(num_total)
+            dist_utils.reduce_mean_(num_total)
         losses, d_preds = self.loss_grad(preds, gt, gt_offsets, assigned, miou, counters, num_total,
                                          H, W)
         self.backward(img, d_preds)
-        if world > 1:
-            dist.all_reduce(self.grads)      # ONE NCCL all-reduce of the flat 303 KB bucket
+        grad_scale = dist_utils.allreduce_bucket_(self.grads)   # ONE all-reduce, 303 KB (yunet_n)
         if step:
-            self.sgd_step(lr, momentum, weight_decay, 1.0 / world)
+            self.sgd_step(lr, momentum, weight_decay, grad_scale)
         return losses
 
     def detect(self, img, score_thr=0.02, iou_thr=0.45, scale_factors=None, max_det=None,
