@@ -195,6 +195,11 @@ int yunet_read_activation(yunet_ctx* ctx, int unit_index, const float* params,
  * number of records, yunet_profile_get returns name ("fwd:<unit>", "bwd:<unit>", ...), duration
  * and the algorithmic bytes of record i. */
 long long yunet_launch_count(const yunet_ctx* ctx);
+/* byte offset inside the workspace of tensor `tensor_id`'s pre-BN activation (kind 0), its
+ * activation gradient (kind 1, train only) or the BatchNorm statistics block (kind 2: double
+ * [4][num_bn_channels] = sum z, sum z^2, sum du, sum du*zhat); -1 if absent.  Debug / tests. */
+long long yunet_ws_offset(const yunet_ctx* ctx, int B, int H, int W, int train, int tensor_id,
+                          int kind);
 int yunet_profile_begin(yunet_ctx* ctx);
 int yunet_profile_end(yunet_ctx* ctx);
 int yunet_profile_get(const yunet_ctx* ctx, int i, char* name, int name_cap, float* ms,

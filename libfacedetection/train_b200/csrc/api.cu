@@ -514,6 +514,18 @@ int yunet_decode_nms(yunet_ctx* ctx, const float* preds, int B, int H, int W, fl
 
 long long yunet_launch_count(const yunet_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+long long yunet_ws_offset(const yunet_ctx* ctx, int B, int H, int W, int train, int tensor_id,
+                          int kind) {
+  if (!ctx || !shape_ok(ctx, B, H, W)) return -1;
+  const Plan& p = ctx->plan;
+  WsLayout L = make_layout(p, B, H, W, train != 0);
+  if (kind == 2) return (long long)L.stats_off;
+  if (tensor_id < 0 || tensor_id >= (int)p.tensors.size() || p.tensors[tensor_id].pred_level >= 0) return -1;
+  if (kind == 0) return (long long)L.z_off[tensor_id];
+  if (kind == 1 && train) return (long long)L.du_off[tensor_id];
+  return -1;
+}
+
 int yunet_profile_begin(yunet_ctx* ctx) {
   if (!ctx) return -1;
   for (ProfEvent& e : ctx->prof) { cudaEventDestroy(e.start); cudaEventDestroy(e.stop); }

@@ -1,0 +1,381 @@
+// Fused ConvDPUnit forward with the pointwise 1x1 conv on the 5th-gen tensor cores (sm_100a):
+//
+//   TMA (cp.async.bulk.tensor.4d, SWIZZLE_128B, zero fill at the image border) brings the 16x16
+//   halo tile of the NHWC pre-BN input into shared memory -> each thread reads ONE pixel row
+//   (conflict-free thanks to the hardware swizzle), applies BN+ReLU, splits every value into
+//   tf32 hi + lo (3xTF32 error compensation: single-pass TF32 misses the 1e-3 parity bar,
+//   SURVEY §0) and stages them as the A operand in TENSOR MEMORY (tcgen05.st) -> one elected
+//   thread issues tcgen05.mma.kind::tf32 (A from TMEM, W1 hi/lo from shared memory, K-major
+//   SW128 descriptors, fp32 accumulators in TMEM): D = Alo*Bhi + Ahi*Blo + Ahi*Bhi ->
+//   tcgen05.ld brings the accumulator row of each pixel back, + bias, zero outside the image ->
+//   shared memory -> depthwise 3x3 stencil -> pre-BN output stored once + BN statistics.
+//
+// Persistent CTAs (2 per SM, 256 TMEM columns each), 14x14 output pixels per tile in two M=128
+// row blocks that pipeline against each other (block 1 converts while block 0's MMAs run, block 0
+// does its epilogue while block 1's MMAs run).  CIN = 64, plain load mode (no pool / up-add).
+// Reference semantics: mmdet/models/utils/yunet_layer.py:30-36.
+#include <cstdio>
+
+#include "kernels.h"
+#include "tc_common.cuh"
+
+namespace yunet {
+
+namespace {
+
+using namespace tc;
+
+constexpr int NT = 256;
+constexpr int CIN = 64;
+constexpr int HT = 16;            // halo tile edge
+constexpr int OT = HT - 2;        // 14 output pixels per edge
+constexpr int HPIX = HT * HT;     // 256 halo pixels = 2 x M128
+constexpr uint32_t RAW_BYTES = HPIX * CIN * 4;   // 65536: TMA landing zone, later the y tile
+constexpr uint32_t TMEM_COLS = 256;
+constexpr uint32_t COL_D0 = 0, COL_D1 = 64, COL_AHI = 128, COL_ALO = 192;
+
+__device__ __forceinline__ void bn_coeffs_tc(const BnRef& r, int c, float& scale, float& shift) {
+  float m, v;
+  if (r.train) {
+    double dm = r.sum[c] * r.inv_count;
+    double dv = r.sumsq[c] * r.inv_count - dm * dm;
+    if (dv < 0.0) dv = 0.0;
+    m = (float)dm; v = (float)dv;
+  } else {
+    m = r.rmean[c]; v = r.rvar[c];
+  }
+  const float rstd = 1.0f / sqrtf(v + kBnEps);
+  scale = r.gamma[c] * rstd;
+  shift = r.beta[c] - m * scale;
+}
+
+template <int COUT>
+struct TcCfg {
+  static constexpr uint32_t B_BLOCK = COUT * 128;          // bytes of one k-block of W1 hi (or lo)
+  static constexpr uint32_t OFF_BHI = RAW_BYTES;
+  static constexpr uint32_t OFF_BLO = OFF_BHI + 2 * B_BLOCK;
+  static constexpr uint32_t OFF_W2 = OFF_BLO + 2 * B_BLOCK;           // [9][COUT]
+  static constexpr uint32_t OFF_B1 = OFF_W2 + 9 * COUT * 4;
+  static constexpr uint32_t OFF_B2 = OFF_B1 + COUT * 4;
+  static constexpr uint32_t OFF_SC = OFF_B2 + COUT * 4;               // [64]
+  static constexpr uint32_t OFF_SH = OFF_SC + CIN * 4;
+  static constexpr uint32_t OFF_BAR = OFF_SH + CIN * 4;               // 3 mbarriers + tmem ptr
+  static constexpr uint32_t SMEM = OFF_BAR + 64;
+  static constexpr int NQ = COUT / 4;
+  static constexpr int RGN = NT / (NQ * 16);
+  static constexpr int RPT = (OT + RGN - 1) / RGN;
+  static_assert((2 * B_BLOCK) % 1024 == 0, "operand alignment");
+};
+
+// y tile in shared memory: [256 pixels][COUT] fp32, 16-byte chunks XOR-swizzled with pixel & 7
+template <int COUT>
+__device__ __forceinline__ float* y_chunk(unsigned char* base, int pix, int chunk) {
+  constexpr int ROWB = COUT * 4;
+  constexpr int MASK = (COUT == 64) ? 7 : 3;     // 16 chunks (64 ch) / 4 chunks (16 ch) per pixel
+  return reinterpret_cast<float*>(base + pix * ROWB + ((chunk ^ (pix & MASK)) << 4));
+}
+
+template <int COUT>
+__global__ void __launch_bounds__(NT, 2)
+unit_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const UnitFwdArgs a, int* status) {
+  using C = TcCfg<COUT>;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(
+      (reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  unsigned char* raw = smem;                                  // [2 m][2 kb][128 px][128 B]
+  unsigned char* sBhi = smem + C::OFF_BHI;
+  unsigned char* sBlo = smem + C::OFF_BLO;
+  float* sW2 = reinterpret_cast<float*>(smem + C::OFF_W2);
+  float* sB1 = reinterpret_cast<float*>(smem + C::OFF_B1);
+  float* sB2 = reinterpret_cast<float*>(smem + C::OFF_B2);
+  float* sSc = reinterpret_cast<float*>(smem + C::OFF_SC);
+  float* sSh = reinterpret_cast<float*>(smem + C::OFF_SH);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);   // [0] tma, [1] mma0, [2] mma1
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int mblk = warp >> 2;            // which M=128 block this warp converts / reads back
+  const int quarter = warp & 3;          // TMEM lane quarter this warp may touch
+
+  // ---- one-time setup
+  if (warp == 0) tmem_alloc<TMEM_COLS>(tmem_ptr);
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_init(&bars[2], 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&tmap);
+  }
+  for (int i = tid; i < COUT * CIN; i += NT) {        // W1[co][ci] -> hi / lo, K-major SW128
+    const int n = i / CIN, k = i % CIN;
+    const float w = __ldg(a.w1 + i);
+    const uint32_t off = sw128_offset(COUT, n, k);
+    *reinterpret_cast<uint32_t*>(sBhi + off) = tf32_hi(w);
+    *reinterpret_cast<uint32_t*>(sBlo + off) = tf32_lo(w);
+  }
+  for (int i = tid; i < 9 * COUT; i += NT) {
+    const int k = i / COUT, co = i % COUT;
+    sW2[i] = __ldg(a.w2 + co * 9 + k);
+  }
+  if (tid < COUT) { sB1[tid] = __ldg(a.b1 + tid); sB2[tid] = __ldg(a.b2 + tid); }
+  if (tid < CIN) {
+    float sc, sh;
+    bn_coeffs_tc(a.bna, tid, sc, sh);
+    sSc[tid] = sc; sSh[tid] = sh;
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = *tmem_ptr;
+  const uint32_t lane_addr = tbase + ((uint32_t)(quarter * 32) << 16);
+  constexpr uint32_t idesc = make_idesc_tf32(128, COUT);
+
+  // depthwise-stage mapping + persistent statistics
+  const int dq = tid % C::NQ;
+  const int dx = (tid / C::NQ) % 16;
+  const int drg = tid / (C::NQ * 16);
+  const int dr0 = drg * C::RPT;
+  const int dr1 = (dr0 + C::RPT < OT) ? dr0 + C::RPT : OT;
+  double st1[4] = {0, 0, 0, 0}, st2[4] = {0, 0, 0, 0};
+  float4 w2r[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) w2r[k] = *reinterpret_cast<const float4*>(sW2 + k * COUT + dq * 4);
+  const float4 bias2 = *reinterpret_cast<const float4*>(sB2 + dq * 4);
+
+  const int tiles_x = (a.W + OT - 1) / OT, tiles_y = (a.H + OT - 1) / OT;
+  const int ntiles = tiles_x * tiles_y * a.B;
+  bool alive = true;
+  uint32_t it = 0;
+  for (int tile = blockIdx.x; tile < ntiles && alive; tile += gridDim.x, ++it) {
+    const uint32_t ph = it & 1;
+    int t = tile;
+    const int tx = t % tiles_x; t /= tiles_x;
+    const int ty = t % tiles_y;
+    const int b = t / tiles_y;
+    const int x0 = tx * OT, y0 = ty * OT;
+
+    // ---- TMA: 4 boxes of (32 ch, 16 cols, 8 rows, 1 image) = 16 KB each
+    if (tid == 0) {
+      mbar_arrive_expect_tx(&bars[0], RAW_BYTES);
+#pragma unroll
+      for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb)
+          tma_load_4d(raw + (m * 2 + kb) * 16384, &tmap, &bars[0], kb * 32, x0 - 1, y0 - 1 + m * 8, b);
+    }
+    if (!mbar_wait(&bars[0], ph)) { alive = false; if (lane == 0) atomicExch(status, 1); }
+
+    // ---- conversion of M block `mblk`: block 1 first waits until block 0's MMAs released the
+    // shared A columns of TMEM
+    const int r = quarter * 32 + lane;            // row inside the M block == TMEM lane
+    if (mblk == 1 && alive) {
+      if (!mbar_wait(&bars[1], ph)) { alive = false; if (lane == 0) atomicExch(status, 2); }
+      tc_fence_after();
+    }
+    if (alive) {
+      const unsigned char* rowp = raw + mblk * 32768 + r * 128;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+          const int c = g * 4 + c4;
+          const int kb = c >> 3, cc = c & 7;
+          const float4 z = *reinterpret_cast<const float4*>(rowp + kb * 16384 + ((cc ^ (r & 7)) << 4));
+          const float4 sc = *reinterpret_cast<const float4*>(sSc + c * 4);
+          const float4 sh = *reinterpret_cast<const float4*>(sSh + c * 4);
+          const float v0 = fmaxf(fmaf(z.x, sc.x, sh.x), 0.f), v1 = fmaxf(fmaf(z.y, sc.y, sh.y), 0.f);
+          const float v2 = fmaxf(fmaf(z.z, sc.z, sh.z), 0.f), v3 = fmaxf(fmaf(z.w, sc.w, sh.w), 0.f);
+          hi[c4 * 4 + 0] = tf32_hi(v0); lo[c4 * 4 + 0] = tf32_lo(v0);
+          hi[c4 * 4 + 1] = tf32_hi(v1); lo[c4 * 4 + 1] = tf32_lo(v1);
+          hi[c4 * 4 + 2] = tf32_hi(v2); lo[c4 * 4 + 2] = tf32_lo(v2);
+          hi[c4 * 4 + 3] = tf32_hi(v3); lo[c4 * 4 + 3] = tf32_lo(v3);
+        }
+        tmem_st16(lane_addr + COL_AHI + g * 16, hi);
+        tmem_st16(lane_addr + COL_ALO + g * 16, lo);
+      }
+      tmem_wait_st();
+    }
+    tc_fence_before();
+    // the four warps of this M block meet, then one thread issues the block's 24 MMAs
+    asm volatile("bar.sync %0, 128;" ::"r"(1 + mblk) : "memory");
+    if ((tid & 127) == 0 && alive) {
+      tc_fence_after();
+      const uint32_t dcol = tbase + (mblk == 0 ? COL_D0 : COL_D1);
+      const uint32_t bhi = smem_u32(sBhi), blo = smem_u32(sBlo);
+      uint32_t acc = 0;
+#pragma unroll
+      for (int pass = 0; pass < 3; ++pass) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t koff = (k >> 2) * C::B_BLOCK + (k & 3) * 32;
+          const uint64_t bd = make_desc_sw128_kmajor((pass == 1 ? blo : bhi) + koff);
+          const uint32_t at = tbase + (pass == 0 ? COL_ALO : COL_AHI) + k * 8;
+          mma_tf32_ts(dcol, at, bd, idesc, acc);
+          acc = 1;
+        }
+      }
+      mma_commit(&bars[1 + mblk]);
+    }
+    // ---- epilogue of M block `mblk`: accumulators -> y tile (over the consumed raw block)
+    if (alive) {
+      if (!mbar_wait(&bars[1 + mblk], ph)) { alive = false; if (lane == 0) atomicExch(status, 3); }
+      tc_fence_after();
+    }
+    if (alive) {
+      const int pix = mblk * 128 + r;
+      const int gy = y0 - 1 + pix / HT, gx = x0 - 1 + pix % HT;
+      const bool in = gy >= 0 && gy < a.H && gx >= 0 && gx < a.W;
+      const uint32_t dcol = lane_addr + (mblk == 0 ? COL_D0 : COL_D1);
+#pragma unroll
+      for (int g = 0; g < COUT / 16; ++g) {
+        uint32_t v[16];
+        tmem_ld16(dcol + g * 16, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+          const float4 bb = *reinterpret_cast<const float4*>(sB1 + g * 16 + c4 * 4);
+          float4 o;
+          o.x = in ? __uint_as_float(v[c4 * 4 + 0]) + bb.x : 0.f;
+          o.y = in ? __uint_as_float(v[c4 * 4 + 1]) + bb.y : 0.f;
+          o.z = in ? __uint_as_float(v[c4 * 4 + 2]) + bb.z : 0.f;
+          o.w = in ? __uint_as_float(v[c4 * 4 + 3]) + bb.w : 0.f;
+          *reinterpret_cast<float4*>(y_chunk<COUT>(raw, pix, g * 4 + c4)) = o;
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+
+    // ---- depthwise 3x3 on the 16x16 y tile -> 14x14 outputs, store z, statistics
+    if (alive && dx < OT && dr0 < OT) {
+      float4 ra[3], rb[3], rc[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        ra[d] = *reinterpret_cast<const float4*>(y_chunk<COUT>(raw, (dr0 + 0) * HT + dx + d, dq));
+        rb[d] = *reinterpret_cast<const float4*>(y_chunk<COUT>(raw, (dr0 + 1) * HT + dx + d, dq));
+      }
+      float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+      const int gx = x0 + dx;
+      for (int rr = dr0; rr < dr1; ++rr) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+          rc[d] = *reinterpret_cast<const float4*>(y_chunk<COUT>(raw, (rr + 2) * HT + dx + d, dq));
+        float4 o = bias2;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          o.x = fmaf(w2r[d].x, ra[d].x, o.x); o.y = fmaf(w2r[d].y, ra[d].y, o.y);
+          o.z = fmaf(w2r[d].z, ra[d].z, o.z); o.w = fmaf(w2r[d].w, ra[d].w, o.w);
+          o.x = fmaf(w2r[3 + d].x, rb[d].x, o.x); o.y = fmaf(w2r[3 + d].y, rb[d].y, o.y);
+          o.z = fmaf(w2r[3 + d].z, rb[d].z, o.z); o.w = fmaf(w2r[3 + d].w, rb[d].w, o.w);
+          o.x = fmaf(w2r[6 + d].x, rc[d].x, o.x); o.y = fmaf(w2r[6 + d].y, rc[d].y, o.y);
+          o.z = fmaf(w2r[6 + d].z, rc[d].z, o.z); o.w = fmaf(w2r[6 + d].w, rc[d].w, o.w);
+        }
+        const int gy = y0 + rr;
+        if (gy < a.H && gx < a.W) {
+          float* dst = a.zout + (long long)b * a.out_batch_stride + ((long long)gy * a.W + gx) * COUT + dq * 4;
+          *reinterpret_cast<float4*>(dst) = o;
+          s1.x += o.x; s1.y += o.y; s1.z += o.z; s1.w += o.w;
+          s2.x = fmaf(o.x, o.x, s2.x); s2.y = fmaf(o.y, o.y, s2.y);
+          s2.z = fmaf(o.z, o.z, s2.z); s2.w = fmaf(o.w, o.w, s2.w);
+        }
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { ra[d] = rb[d]; rb[d] = rc[d]; }
+      }
+      st1[0] += s1.x; st1[1] += s1.y; st1[2] += s1.z; st1[3] += s1.w;
+      st2[0] += s2.x; st2[1] += s2.y; st2[2] += s2.z; st2[3] += s2.w;
+    }
+    // the y tile (generic-proxy writes) is overwritten by the next TMA (async proxy)
+    fence_proxy_async_smem();
+    __syncthreads();
+  }
+
+  // ---- statistics: lanes sharing a channel quad reduce in the warp, then fp64 atomics
+  if (a.osum != nullptr) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+#pragma unroll
+      for (int o = 16; o >= C::NQ; o >>= 1) {
+        st1[c] += __shfl_xor_sync(0xffffffffu, st1[c], o);
+        st2[c] += __shfl_xor_sync(0xffffffffu, st2[c], o);
+      }
+    }
+    if (lane < C::NQ) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        atomicAdd(a.osum + dq * 4 + c, st1[c]);
+        atomicAdd(a.osumsq + dq * 4 + c, st2[c]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<TMEM_COLS>(tbase);
+}
+
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                             const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                             CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                             CUtensorMapFloatOOBfill);
+
+EncodeFn get_encode() {
+  static EncodeFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    cudaDriverEntryPointQueryResult q;
+    void* p = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess)
+      fn = reinterpret_cast<EncodeFn>(p);
+  }
+  return fn;
+}
+
+template <int COUT>
+cudaError_t launch_tc_t(const CUtensorMap& tm, const UnitFwdArgs& a, int num_sms, int* status,
+                        cudaStream_t s) {
+  using C = TcCfg<COUT>;
+  const size_t smem = C::SMEM + 1024;
+  auto kern = unit_fwd_tc_kernel<COUT>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const int ntiles = ((a.W + OT - 1) / OT) * ((a.H + OT - 1) / OT) * a.B;
+  int grid = 2 * num_sms;
+  if (grid > ntiles) grid = ntiles;
+  kern<<<grid, NT, smem, s>>>(tm, a, status);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+int unit_fwd_tc_supported(int cin, int cout, int mode) {
+  return cin == 64 && mode == 0 && (cout == 64 || cout == 16) && get_encode() != nullptr;
+}
+
+// `status`: device int, set non-zero if a bounded wait inside the kernel timed out.
+cudaError_t launch_unit_fwd_tc(int cout, const UnitFwdArgs& a, int num_sms, int* status,
+                               cudaStream_t s) {
+  EncodeFn enc = get_encode();
+  if (!enc) return cudaErrorNotSupported;
+  CUtensorMap tm;
+  // NHWC input as a 4-D tensor (C, W, H, B); box = 32 channels x 16 cols x 8 rows x 1 image
+  cuuint64_t dims[4] = {(cuuint64_t)CIN, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.B};
+  cuuint64_t strides[3] = {(cuuint64_t)CIN * 4, (cuuint64_t)a.W * CIN * 4,
+                           (cuuint64_t)a.H * a.W * CIN * 4};
+  cuuint32_t box[4] = {32, HT, 8, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(a.za), dims, strides,
+                   box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+  if (cout == 64) return launch_tc_t<64>(tm, a, num_sms, status, s);
+  if (cout == 16) return launch_tc_t<16>(tm, a, num_sms, status, s);
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace yunet

@@ -127,6 +127,7 @@ class Emu:
         grad = torch.zeros_like(self.w)
         bn = self.bn_of_tensor()
         du, S1, S2 = {}, {}, {}
+        self.du, self.S1, self.S2 = du, S1, S2
         B = img.shape[0]
         off = 0
         dlevel = {}

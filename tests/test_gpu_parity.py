@@ -115,6 +115,57 @@ def test_priors_index_exact():
         assert torch.equal(eng.grid_priors(size, size).cpu(), ref)
 
 
+
+def _oracle_grads(arch, img_np, gb, gl, gk, assigned, miou, dtype):
+    """Oracle losses + parameter gradients with the given assignment injected (so value parity is
+    independent of tie-breaking); dtype float32 = the reference arithmetic, float64 = ground truth."""
+    P, Bf = _weights(arch)
+    Pg = {k: v.to(dtype).clone().requires_grad_(True) for k, v in P.items()}
+    Bf = {k: (v.to(dtype) if v.dtype.is_floating_point else v.clone()) for k, v in Bf.items()}
+    outs = orc.model_forward(torch.from_numpy(img_np).to(dtype), Pg, Bf, arch, training=True)
+    orig = orc.simota_assign
+    it = iter(range(len(gb)))
+
+    def forced(*a, **k):
+        b = next(it)
+        ov = torch.where(assigned[b] > 0, miou[b].to(dtype), torch.full_like(miou[b], -1e5).to(dtype))
+        return assigned[b].clone(), ov
+
+    orc.simota_assign = forced
+    try:
+        losses = orc.head_loss(*outs, [torch.from_numpy(x) for x in gb],
+                               [torch.from_numpy(x) for x in gl], [torch.from_numpy(x) for x in gk])
+    finally:
+        orc.simota_assign = orig
+    sum(losses.values()).backward()
+    return {k: float(v) for k, v in losses.items()}, {k: v.grad.detach() for k, v in Pg.items()}
+
+
+def _check_grads(tag, mine, ref32, truth64):
+    """Per tensor: within TOL of the fp32 reference, OR at least as close to the float64 ground
+    truth as the reference's own fp32 evaluation is (x2) — deep-layer sums over 10^5..10^6 pixels
+    cancel heavily, so two correct fp32 evaluations can differ by more than 1e-3 of the result."""
+    gmax = max(float(v.abs().max()) for v in ref32.values())
+    atol = 1e-5 * gmax
+    rows, bad = [], []
+    for k, v in mine.items():
+        m = v.detach().double().cpu()
+        r, t = ref32[k].double(), truth64[k].double()
+        scale = float(t.abs().max())
+        e_ref = float((m - r).abs().max())
+        e_mine_t = float((m - t).abs().max())
+        e_ref_t = float((r - t).abs().max())
+        ok = e_ref <= TOL * scale + atol or e_mine_t <= max(TOL * scale, 2.0 * e_ref_t) + atol
+        rows.append((e_mine_t / (scale + atol), k, e_ref / (scale + atol), e_ref_t / (scale + atol)))
+        if not ok:
+            bad.append(k)
+    rows.sort(reverse=True)
+    print(f'{tag}: worst tensors (mine-vs-f64, name, mine-vs-ref32, ref32-vs-f64):')
+    for r in rows[:8]:
+        print(f'   {r[0]:.3e}  {r[1]:55s} {r[2]:.3e} {r[3]:.3e}')
+    assert not bad, f'gradient parity failed for {bad}'
+
+
 # --------------------------------------------------------------------------------- SimOTA + loss
 def _tie_equivalent(assigned_mine, assigned_ref, dbg):
     """Same assignment up to a swap between candidates whose cost for that gt is identical in fp32
@@ -198,21 +249,16 @@ def test_train_step_matches_reference_golden(arch, seed):
     for i, k in enumerate(('loss_cls', 'loss_bbox', 'loss_obj', 'loss_kps')):
         assert abs(mine_l[i] - ref_l[i]) <= TOL * max(1.0, abs(ref_l[i])), (k, mine_l[i], ref_l[i])
     grads = eng.param_views(eng.grads)
-    gmax = max(float(np.abs(g['grad/' + k]).max()) for k in grads)
-    worst = 0.0
-    for k, v in grads.items():
-        ref = torch.from_numpy(g['grad/' + k])
-        scale = float(ref.abs().max())
-        err = float((v.cpu() - ref).abs().max())
-        # biases that feed a train-mode BatchNorm have an exactly-zero true gradient; the reference
-        # value is rounding residue, so compare on the scale of the whole gradient
-        atol = 1e-5 * gmax
-        assert err <= TOL * scale + atol, f'{k}: err {err:.3e} scale {scale:.3e}'
-        worst = max(worst, err / (scale + atol))
-    print(f'{arch}: worst normalised grad err {worst:.3e}')
+    ref32 = {k: torch.from_numpy(g['grad/' + k]) for k in grads}
+    a_t = torch.from_numpy(g['assigned_gt_inds']).long()
+    ov_t = torch.from_numpy(g['max_overlaps'])
+    _, truth = _oracle_grads(arch, synthetic.make_images(B, size, seed), gb, gl, gk, a_t, ov_t,
+                             torch.float64)
+    _check_grads(arch, grads, ref32, truth)
     eng.sgd_step(0.01, 0.9, 0.0005, 1.0)
     sd = eng.state_dict()
     for k in grads:
+        # parameters after one SGD step (lr 0.01): a 1e-3 gradient deviation moves them by <1e-5
         assert _rel(sd[k], g['after/' + k]) < TOL, k
     for k in sd:
         if 'running_' in k:
@@ -235,40 +281,15 @@ def test_loss_and_grads_match_oracle(arch):
                                     eng._bufs[('miou', (B, preds.shape[1]), torch.float32)], counters,
                                     counters, size, size)
     eng.backward(img, d_preds)
-    # oracle with the kernel's assignment injected
-    P, Bf = _weights(arch)
-    Pg = {k: v.clone().requires_grad_(True) for k, v in P.items()}
-    outs = orc.model_forward(torch.from_numpy(img_np), Pg, Bf, arch, training=True)
-    orig = orc.simota_assign
-    it = iter(range(B))
-
-    def forced(*a, **k):
-        b = next(it)
-        ov = torch.where(assigned[b] > 0, miou[b], torch.full_like(miou[b], -1e5))
-        return assigned[b].clone(), ov
-
-    orc.simota_assign = forced
-    try:
-        ref_losses = orc.head_loss(*outs, [torch.from_numpy(x) for x in gb],
-                                   [torch.from_numpy(x) for x in gl],
-                                   [torch.from_numpy(x) for x in gk])
-    finally:
-        orc.simota_assign = orig
-    sum(ref_losses.values()).backward()
+    # oracle with the kernel's assignment injected, fp32 (reference arithmetic) and fp64 (truth)
+    ref_losses, ref32 = _oracle_grads(arch, img_np, gb, gl, gk, assigned, miou, torch.float32)
+    _, truth = _oracle_grads(arch, img_np, gb, gl, gk, assigned, miou, torch.float64)
     mine_l = losses.cpu().numpy()
     for i, k in enumerate(('loss_cls', 'loss_bbox', 'loss_obj', 'loss_kps')):
-        r = float(ref_losses[k])
+        r = ref_losses[k]
         assert abs(mine_l[i] - r) <= TOL * max(1.0, abs(r)), (k, mine_l[i], r)
-    grads = eng.param_views(eng.grads)
-    gmax = max(float(Pg[k].grad.abs().max()) for k in grads)
-    worst = 0.0
-    for k, v in grads.items():
-        ref = Pg[k].grad
-        scale = float(ref.abs().max())
-        err = float((v.cpu() - ref).abs().max())
-        assert err <= TOL * scale + 1e-5 * gmax, f'{k}: err {err:.3e} scale {scale:.3e}'
-        worst = max(worst, err / (scale + 1e-5 * gmax))
-    print(f'{arch}: losses {mine_l}, worst normalised grad err {worst:.3e}')
+    print(f'{arch}: losses {mine_l}')
+    _check_grads(arch, eng.param_views(eng.grads), ref32, truth)
 
 
 # --------------------------------------------------------------------------------- decode + NMS
@@ -302,7 +323,12 @@ def test_nms_on_real_forward_and_empty():
     dets, counts, _ = eng.detect(img)
     assert int(counts[0]) == g['dets'].shape[0]
     if g['dets'].shape[0]:
-        np.testing.assert_allclose(dets[0, :int(counts[0])].cpu().numpy(), g['dets'], rtol=1e-3, atol=1e-2)
+        # scores that differ in the last ulp (GPU expf vs CPU) may swap neighbours in the score
+        # order: compare as sets (sorted by coordinates), scores stay sorted
+        mine = dets[0, :int(counts[0])].cpu().numpy()
+        assert bool((mine[:-1, 4] >= mine[1:, 4]).all())
+        key = lambda d: d[np.lexsort((d[:, 1], d[:, 0]))]
+        np.testing.assert_allclose(key(mine), key(g['dets']), rtol=1e-3, atol=1e-2)
     # all-background logits -> zero detections, no crash
     preds = torch.full((2, 2100, 16), -20.0).cuda()
     _, c, _ = eng.decode_nms(preds, 320, 320)
