@@ -80,6 +80,7 @@ def _load():
         'yunet_unit_get': (ci, [vp, ci, P(UnitDesc)]),
         'yunet_read_activation': (ci, [vp, ci, vp, vp, ci, ci, ci, ci, vp, vp, vp]),
         'yunet_launch_count': (ll, [vp]),
+        'yunet_set_option': (ci, [vp, C.c_char_p, ci]),
         'yunet_ws_offset': (ll, [vp, ci, ci, ci, ci, ci, ci]),
         'yunet_profile_begin': (ci, [vp]),
         'yunet_profile_end': (ci, [vp]),

@@ -25,6 +25,7 @@ struct yunet_ctx {
   int num_sms = 148;
   bool sms_known = false;
   long long launches = 0;       // kernels launched by this ctx (bench.py's gpu_launches)
+  int opt_tc_forward = 0;       // use the tcgen05 unit kernel where it applies
   bool profiling = false;
   std::vector<ProfEvent> prof;
   std::vector<float> prof_ms;
@@ -73,6 +74,7 @@ struct Views {
 
   float* z(int t) const { return reinterpret_cast<float*>(ws + L.z_off[t]); }
   float* du(int t) const { return reinterpret_cast<float*>(ws + L.du_off[t]); }
+  int* status() const { return reinterpret_cast<int*>(ws + L.status_off); }
   double* stat(int which) const {
     return reinterpret_cast<double*>(ws + L.stats_off) + (size_t)which * p.num_bn_ch;
   }
@@ -284,9 +286,14 @@ int yunet_forward(yunet_ctx* ctx, const float* img, const float* params, float* 
   cudaStream_t s = (cudaStream_t)stream;
   Views v{p, L, (char*)ws, params, bn_running, preds, nullptr, B, H, W, train};
   cudaError_t e;
+  ensure_sms(ctx);
   if (train) {
     e = cudaMemsetAsync((char*)ws + L.stats_off, 0, L.stats_bytes, s);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "forward: memset statistics");
+  }
+  if (ctx->opt_tc_forward) {
+    e = cudaMemsetAsync((char*)ws + L.status_off, 0, 256, s);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "forward: memset status");
   }
   {
     StemArgs a;
@@ -326,8 +333,10 @@ int yunet_forward(yunet_ctx* ctx, const float* img, const float* params, float* 
       const double hw = (double)a.H * a.W;
       double bytes = 4.0 * B * (u.cin * hw * (u.mode == LOAD_POOL ? 4.0 : 1.0) + u.cout * hw);
       if (u.mode == LOAD_UPADD) bytes += 4.0 * B * u.cin * hw / 4.0;
-      Scope sc(ctx, s, "fwd:" + u.name, bytes);
-      e = launch_unit_fwd(u.cin, u.cout, u.mode, a, s);
+      const bool tc = ctx->opt_tc_forward && unit_fwd_tc_supported(u.cin, u.cout, u.mode);
+      Scope sc(ctx, s, (tc ? "fwd_tc:" : "fwd:") + u.name, bytes);
+      e = tc ? launch_unit_fwd_tc(u.cout, a, ctx->num_sms, v.status(), s)
+             : launch_unit_fwd(u.cin, u.cout, u.mode, a, s);
     }
     if (e != cudaSuccess) return fail(ctx, (int)e, "forward: unit %s: %s", u.name.c_str(), cudaGetErrorString(e));
   }
@@ -514,12 +523,19 @@ int yunet_decode_nms(yunet_ctx* ctx, const float* preds, int B, int H, int W, fl
 
 long long yunet_launch_count(const yunet_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+int yunet_set_option(yunet_ctx* ctx, const char* name, int value) {
+  if (!ctx || !name) return -1;
+  if (strcmp(name, "tc_forward") == 0) { ctx->opt_tc_forward = value ? 1 : 0; return 0; }
+  return fail(ctx, -1, "unknown option %s", name);
+}
+
 long long yunet_ws_offset(const yunet_ctx* ctx, int B, int H, int W, int train, int tensor_id,
                           int kind) {
   if (!ctx || !shape_ok(ctx, B, H, W)) return -1;
   const Plan& p = ctx->plan;
   WsLayout L = make_layout(p, B, H, W, train != 0);
   if (kind == 2) return (long long)L.stats_off;
+  if (kind == 3) return (long long)L.status_off;
   if (tensor_id < 0 || tensor_id >= (int)p.tensors.size() || p.tensors[tensor_id].pred_level >= 0) return -1;
   if (kind == 0) return (long long)L.z_off[tensor_id];
   if (kind == 1 && train) return (long long)L.du_off[tensor_id];

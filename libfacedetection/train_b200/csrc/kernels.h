@@ -102,6 +102,11 @@ cudaError_t launch_grid_priors(float* priors, const int* lh, const int* lw, cons
                                cudaStream_t s);
 int unit_fwd_supported(int cin, int cout);
 
+// ---- unit_fwd_tc.cu: tcgen05 / TMEM / TMA version of the fused unit (CIN = 64, plain load) ----
+int unit_fwd_tc_supported(int cin, int cout, int mode);
+cudaError_t launch_unit_fwd_tc(int cout, const UnitFwdArgs& a, int num_sms, int* status,
+                               cudaStream_t s);
+
 // ---- launchers (kernels_bwd.cu) ----
 cudaError_t launch_unit_bwd(int cin, int cout, int mode, const UnitBwdArgs& a, int num_sms,
                             cudaStream_t s);

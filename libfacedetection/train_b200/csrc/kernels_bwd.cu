@@ -200,7 +200,10 @@ __global__ void __launch_bounds__(NT, 1) unit_bwd_kernel(const UnitBwdArgs a) {
       constexpr int Q = COUT / 4;
       const float* dimg = a.dout + (long long)b * a.dout_batch_stride;
       const float* zimg = HAS_BN ? a.zout + (long long)b * a.H * a.W * COUT : nullptr;
-      for (int i = tid; i < HP * Q; i += NT) {
+#pragma unroll 4
+      for (int it = 0; it < (HP * Q + NT - 1) / NT; ++it) {
+        const int i = tid + it * NT;
+        if (i >= HP * Q) break;
         const int pix = i / Q, q = i % Q;
         const int gy = y0 + pix / HW - 1, gx = x0 + pix % HW - 1;
         float4 g = f4(0.f);
@@ -224,7 +227,9 @@ __global__ void __launch_bounds__(NT, 1) unit_bwd_kernel(const UnitBwdArgs a) {
     // ---- S0b: activated input on the interior tile
     {
       constexpr int Q = CIN / 4;
-      for (int i = tid; i < TP * Q; i += NT) {
+#pragma unroll 4
+      for (int it = 0; it < TP * Q / NT; ++it) {
+        const int i = tid + it * NT;
         const int pix = i / Q, q = i % Q;
         const int gy = y0 + pix / TW, gx = x0 + pix % TW;
         float4 v = f4(0.f);

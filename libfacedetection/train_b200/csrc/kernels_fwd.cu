@@ -110,7 +110,9 @@ __global__ void __launch_bounds__(NT, 2) unit_fwd_kernel(const UnitFwdArgs a) {
   const int x0 = tx * TW, y0 = ty * TH;
 
   // ---- stage 0: weights + BN coefficients into shared memory
-  for (int i = tid; i < CIN * COUT; i += NT) {
+#pragma unroll
+  for (int it = 0; it < CIN * COUT / NT; ++it) {
+    const int i = tid + it * NT;
     int ci = i / COUT, co = i % COUT;
     sW1t[i] = __ldg(a.w1 + co * CIN + ci);
   }
@@ -133,7 +135,12 @@ __global__ void __launch_bounds__(NT, 2) unit_fwd_kernel(const UnitFwdArgs a) {
   // ---- stage 1: halo tile of activated inputs -> sA
   {
     constexpr int Q = CIN / 4;
-    for (int i = tid; i < HPP * Q; i += NT) {
+    static_assert((HPP * Q) % NT == 0, "prologue trip count");
+    // fixed trip count + partial unroll: the global loads of several iterations are in flight
+    // together instead of one dependent load per iteration
+#pragma unroll 4
+    for (int it = 0; it < HPP * Q / NT; ++it) {
+      const int i = tid + it * NT;
       const int pix = i / Q, q = i % Q;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (pix < HP) {

@@ -235,6 +235,8 @@ WsLayout make_layout(const Plan& p, int B, int H, int W, bool train) {
   L.stats_off = cur;
   L.stats_bytes = sizeof(double) * 4 * (size_t)p.num_bn_ch;
   cur = align(cur + L.stats_bytes);
+  L.status_off = cur;
+  cur = align(cur + 256);
   L.total = cur;
   int off = 0;
   for (int l = 0; l < 3; ++l) {

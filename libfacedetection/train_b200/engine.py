@@ -64,6 +64,17 @@ class YuNetEngine:
         self.momentum = 0.1   # BatchNorm momentum (torch default)
         self.launches_per_train_step = None
 
+    def set_option(self, name, value):
+        """Library options: ``tc_forward`` (tcgen05/TMEM/TMA unit kernel for the 64-channel
+        plain-load units)."""
+        check(self.h, lib.yunet_set_option(self.h, name.encode(), int(value)), 'yunet_set_option')
+
+    def status_flags(self, B, H, W, train):
+        """Device-side error flags of the tensor-core kernels (all zero = ok)."""
+        off = lib.yunet_ws_offset(self.h, B, H, W, 1 if train else 0, 0, 3)
+        ws = self.workspace(B, H, W, train)
+        return ws[off:off + 256].view(torch.int32).cpu()
+
     # ------------------------------------------------------------------ parameters
     def param_views(self, bucket=None):
         bucket = self.params if bucket is None else bucket

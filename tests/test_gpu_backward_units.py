@@ -46,6 +46,7 @@ def test_backward_intermediates(arch):
     stats = _ws_tensor(eng, B, H, W, 0, 2, (4, nbn), torch.float64).cpu()
     bn_off = {name: off for name, off, ch in eng.ctx.bns()}
     rows = []
+    bad_dump = []
     # tensors in backward order: what each unit's backward WROTE (du of its inputs)
     seen = set()
     order = []
@@ -67,6 +68,23 @@ def test_backward_intermediates(arch):
         s1 = float((stats[2, o:o + Cc] - emu.S1[t]).abs().max() / (emu.S1[t].abs().max() + 1e-30))
         s2 = float((stats[3, o:o + Cc] - emu.S2[t]).abs().max() / (emu.S2[t].abs().max() + 1e-30))
         rows.append((f'du[t{t}] first written by {writer}', e, s1, s2))
+        if e > 1e-4 and not bad_dump:
+            bad_dump.append(t)
+            d = (mine - ref).abs()
+            scale = float(ref.abs().max())
+            print(f'--- first bad tensor t{t} ({writer}): shape {tuple(ref.shape)}')
+            pc = d.amax((0, 1, 2)) / scale
+            print('    err by channel:', ' '.join(f'{float(x):.1e}' for x in pc))
+            pm = d.amax(-1) / scale          # (B,H,W)
+            for b in range(pm.shape[0]):
+                print(f'    image {b}: err by pixel (rows), x->')
+                for y in range(pm.shape[1]):
+                    print('      ' + ' '.join('#' if float(v) > 1e-3 else ('+' if float(v) > 1e-5 else '.') for v in pm[b, y]))
+            # second launch: determinism
+            eng.backward(img.cuda(), d_preds.cuda())
+            torch.cuda.synchronize()
+            again = _ws_tensor(eng, B, H, W, t, 1, tuple(ref.shape)).cpu().double()
+            print('    identical on a second backward:', bool(torch.equal(again, mine)))
     print('\nactivation gradients (rel err), sum(du), sum(du*zhat):')
     for r in rows:
         print(f'   {r[0]:62s} {r[1]:.2e} {r[2]:.2e} {r[3]:.2e}')

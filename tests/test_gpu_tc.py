@@ -1,0 +1,68 @@
+"""GPU: the tcgen05 / TMEM / TMA unit kernel (3xTF32) against the exact-fp32 CUDA-core path of the
+same library and against the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from conftest import GOLDEN  # noqa: E402
+from oracle import yunet_oracle as orc  # noqa: E402
+
+
+def _engine(arch):
+    from libfacedetection.train_b200 import YuNetEngine
+    eng = YuNetEngine(arch)
+    d = np.load(os.path.join(GOLDEN, f'weights_{arch}.npz'))
+    eng.load_state_dict({k: torch.from_numpy(d[k]) for k in d.files})
+    return eng
+
+
+def _rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+@pytest.mark.parametrize('arch', ['yunet_n', 'yunet_s'])
+@pytest.mark.parametrize('train', [False, True])
+@pytest.mark.parametrize('shape', [(3, 96, 160), (2, 320, 320)])
+def test_tc_forward_equals_fp32_path(arch, train, shape):
+    B, H, W = shape
+    eng = _engine(arch)
+    rng = np.random.default_rng(21)
+    img = torch.from_numpy(rng.random((B, 3, H, W), dtype=np.float32) * 255).cuda()
+    eng.set_option('tc_forward', 0)
+    ref = eng.forward(img, train=train).clone()
+    ref_units = [eng.read_activation(i, B, H, W, train=train).clone()
+                 for i, u in enumerate(eng.ctx.units()) if u.pred_level < 0]
+    eng.set_option('tc_forward', 1)
+    out = eng.forward(img, train=train)
+    torch.cuda.synchronize()
+    flags = eng.status_flags(B, H, W, train)
+    assert int(flags.abs().sum()) == 0, f'tensor-core kernel reported {flags[:4].tolist()}'
+    k = 0
+    worst = 0.0
+    for i, u in enumerate(eng.ctx.units()):
+        if u.pred_level >= 0:
+            continue
+        e = _rel(eng.read_activation(i, B, H, W, train=train), ref_units[k])
+        k += 1
+        worst = max(worst, e)
+        assert e < 1e-4, f'unit {i} {u.name.decode()}: {e:.3e}'
+    e = _rel(out, ref)
+    print(f'{arch} train={train} {shape}: tc vs fp32 preds {e:.3e}, worst unit {worst:.3e}')
+    assert e < 1e-4
+
+
+def test_tc_forward_matches_reference_golden():
+    g = np.load(os.path.join(GOLDEN, 'forward_yunet_n_640.npz'))
+    eng = _engine('yunet_n')
+    eng.set_option('tc_forward', 1)
+    torch.manual_seed(0)
+    img = (torch.rand(1, 3, 640, 640) * 255).cuda()
+    preds = eng.forward(img, train=False)
+    e = _rel(preds, torch.from_numpy(g['preds']))
+    print(f'tc forward vs reference golden (640): {e:.3e}')
+    assert e < 1e-3
