@@ -286,9 +286,10 @@ unit_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const UnitFwdArgs a
       st1[0] += s1.x; st1[1] += s1.y; st1[2] += s1.z; st1[3] += s1.w;
       st2[0] += s2.x; st2[1] += s2.y; st2[2] += s2.z; st2[3] += s2.w;
     }
-    // the y tile (generic-proxy writes) is overwritten by the next TMA (async proxy)
+    // the y tile (generic-proxy writes) is overwritten by the next TMA (async proxy); the
+    // barrier also makes the (error-path) exit decision uniform across the CTA
     fence_proxy_async_smem();
-    __syncthreads();
+    alive = __syncthreads_and(alive ? 1 : 0) != 0;
   }
 
   // ---- statistics: lanes sharing a channel quad reduce in the warp, then fp64 atomics

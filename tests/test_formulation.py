@@ -66,7 +66,15 @@ class Emu:
         C = self.z[t].shape[-1]
         mean, rstd = self.coef(t)
         g, b = self.w[gamma_off:gamma_off + C], self.w[beta_off:beta_off + C]
-        return torch.relu((self.z[t] - mean) * rstd * g + b)
+        u = (self.z[t] - mean) * rstd * g + b
+        m = u > 0
+        ov = getattr(self, 'mask_override', None)
+        if ov is not None and t in ov:
+            # rounding-fragile elements (|u| ~ 0): follow the fp32 kernels' ReLU decision
+            m = torch.where(u.abs() < 1e-4, ov[t], m)
+        self.mask = getattr(self, 'mask', {})
+        self.mask[t] = m
+        return u * m
 
     def bn_of_tensor(self):
         m = {self.stem.out: (self.stem.gamma, self.stem.beta)}
@@ -177,9 +185,10 @@ class Emu:
             grad[u.w1:u.w1 + u.cout * u.cin] = torch.einsum('bhwo,bhwi->oi', dy, a).reshape(-1)
             h = dy @ W1
             # ---- prologue backward
-            ua = self.act(u.in_a, *bn[u.in_a])          # relu(u) > 0  <=>  u > 0
+            ua = self.act(u.in_a, *bn[u.in_a])
+            ma = self.mask[u.in_a]
             if u.mode in (0, 2):
-                contrib = h * (ua > 0)
+                contrib = h * ma
             else:
                 Bn, H2, W2_, C = ua.shape
                 win = ua.reshape(Bn, H2 // 2, 2, W2_ // 2, 2, C).permute(0, 1, 3, 5, 2, 4).reshape(
@@ -189,7 +198,9 @@ class Emu:
                 mx = win.amax(-1, keepdim=True)
                 first = (win == mx).double()
                 first = first * (first.cumsum(-1) == 1)
-                hv = (h * (mx.squeeze(-1) > 0)).unsqueeze(-1) * first
+                mwin = ma.reshape(Bn, H2 // 2, 2, W2_ // 2, 2, C).permute(0, 1, 3, 5, 2, 4).reshape(
+                    Bn, H2 // 2, W2_ // 2, C, 4).double()
+                hv = (h * ((mwin * first).sum(-1) > 0)).unsqueeze(-1) * first
                 contrib = hv.reshape(Bn, H2 // 2, W2_ // 2, C, 2, 2).permute(0, 1, 4, 2, 5, 3).reshape(
                     Bn, H2, W2_, C)
             if u.acc_a:
@@ -199,10 +210,10 @@ class Emu:
                 du[u.in_a] = contrib
             add_stats(u.in_a, contrib)
             if u.mode == 2:
-                ub = self.act(u.in_b, *bn[u.in_b])
+                self.act(u.in_b, *bn[u.in_b])
                 Bn, Hh, Wh, C = h.shape
                 hs = h.reshape(Bn, Hh // 2, 2, Wh // 2, 2, C).sum((2, 4))
-                cb = hs * (ub > 0)
+                cb = hs * self.mask[u.in_b]
                 if u.acc_b:
                     du[u.in_b] = du[u.in_b] + cb
                 else:

@@ -33,8 +33,17 @@ def test_backward_intermediates(arch):
     img = torch.from_numpy(rng.random((B, 3, H, W), dtype=np.float32) * 255)
     flat = _flat_params(eng.ctx, P)
     emu = Emu(eng.ctx, flat, B, H, W)
-    ref_preds = emu.forward(img)
     preds = eng.forward(img.cuda(), train=True)
+    # ReLU decisions of the fp32 kernels, used by the float64 emulation only where |u| < 1e-4
+    # (there rounding decides the branch; a single flip moves all upstream gradients by ~1e-2)
+    units_all = eng.ctx.units()
+    ov = {eng.ctx.units(include_stem=True)[0].out:
+          eng.read_activation(-1, B, H, W, train=True).permute(0, 2, 3, 1).cpu() > 0}
+    for i, u in enumerate(units_all):
+        if u.has_bn:
+            ov[u.out] = eng.read_activation(i, B, H, W, train=True).permute(0, 2, 3, 1).cpu() > 0
+    emu.mask_override = ov
+    ref_preds = emu.forward(img)
     assert float((preds.cpu().double() - ref_preds).abs().max() / ref_preds.abs().max()) < 1e-4
     d_preds = torch.from_numpy(rng.standard_normal(tuple(ref_preds.shape)).astype(np.float32))
     ref_grad = emu.backward(img, d_preds)
@@ -101,4 +110,14 @@ def test_backward_intermediates(arch):
     for e, n in prow[:10]:
         print(f'   {e:.2e} {n}')
     assert max(r[1] for r in rows) < 1e-4 and max(r[2] for r in rows) < 1e-3
-    assert prow[0][0] < 1e-3
+    # tensors with an identically-zero true gradient (conv biases in front of a train-mode BN) hold
+    # fp32 rounding residue only: bounded relative to the whole gradient instead
+    for name, off, shape in eng.ctx.params():
+        n = int(np.prod(shape))
+        r = ref_grad[off:off + n]
+        err = float((g[off:off + n] - r).abs().max())
+        scale = float(r.abs().max())
+        if scale < 1e-6 * gmax:
+            assert err < 1e-4 * gmax, (name, err)
+        else:
+            assert err < 1e-3 * scale + 1e-5 * gmax, (name, err, scale)
