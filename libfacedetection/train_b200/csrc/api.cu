@@ -25,7 +25,7 @@ struct yunet_ctx {
   int num_sms = 148;
   bool sms_known = false;
   long long launches = 0;       // kernels launched by this ctx (bench.py's gpu_launches)
-  int opt_tc_forward = 0;       // use the tcgen05 unit kernel where it applies
+  int opt_tc_forward = 1;       // use the tcgen05 unit kernel where it applies (default on)
   bool profiling = false;
   std::vector<ProfEvent> prof;
   std::vector<float> prof_ms;

@@ -120,33 +120,52 @@ FRAGILE = 1e-4   # |u| below this (u = BN output, O(1)) makes the ReLU branch a 
 
 
 def _engine_masks(eng, B, H, W):
-    """ReLU decisions the kernels took in the last train-mode forward, per BN unit (NCHW bool)."""
-    masks = {'stem': eng.read_activation(-1, B, H, W, train=True).cpu() > 0}
+    """Post-ReLU activations of the last train-mode forward, per BN unit (NCHW): they carry the
+    ReLU decisions (a > 0) and the max-pool winners the kernels took."""
+    acts = {'stem': eng.read_activation(-1, B, H, W, train=True).cpu()}
     for i, u in enumerate(eng.ctx.units()):
         if u.has_bn:
-            masks[u.name.decode()] = eng.read_activation(i, B, H, W, train=True).cpu() > 0
-    return masks
+            acts[u.name.decode()] = eng.read_activation(i, B, H, W, train=True).cpu()
+    return acts
 
 
 class _MaskedOracle:
     """Context manager: evaluate the oracle on the same branch of the piecewise-linear network as
-    the kernels.  Where the BN output u is within FRAGILE of zero, fp32 rounding decides the ReLU
-    branch (both are legitimate evaluations of the reference function; one flipped element moves
-    every upstream gradient by ~1e-2 through the BatchNorm-backward means), so there the oracle
-    takes the kernel's decision; everywhere else it keeps its own u > 0."""
+    the kernels.  Where the BN output u is within FRAGILE of zero (ReLU), or the two largest
+    values of a 2x2 pooling window are within 1e-5 of each other (max-pool winner), fp32 rounding
+    decides the branch — both are legitimate evaluations of the reference function, but one flipped
+    element moves every upstream gradient by ~1e-2 through the BatchNorm-backward means.  There the
+    oracle takes the kernels' decision; everywhere else it keeps its own."""
 
-    def __init__(self, masks):
-        self.masks, self.overrides, self.total = masks, 0, 0
+    def __init__(self, acts):
+        self.acts, self.overrides, self.pool_overrides, self.total = acts, 0, 0, 0
+        self.last_key = None
 
     def _relu(self, u, key):
         own = u > 0
-        if self.masks is None:
+        self.last_key = key
+        if self.acts is None:
             return u * own
         fragile = u.abs() < FRAGILE
-        m = torch.where(fragile, self.masks[key], own)
+        m = torch.where(fragile, self.acts[key] > 0, own)
         self.overrides += int((m != own).sum())
         self.total += own.numel()
         return u * m
+
+    def _pool(self, x):
+        N, C, H, W = x.shape
+        win = x.reshape(N, C, H // 2, 2, W // 2, 2).permute(0, 1, 2, 4, 3, 5).reshape(N, C, H // 2, W // 2, 4)
+        idx = win.argmax(-1)
+        if self.acts is not None:
+            kw = self.acts[self.last_key].to(x.dtype).reshape(N, C, H // 2, 2, W // 2, 2) \
+                .permute(0, 1, 2, 4, 3, 5).reshape(N, C, H // 2, W // 2, 4)
+            top = win.topk(2, -1).values
+            fragile = (top[..., 0] - top[..., 1]) < 1e-5 * top[..., 0].abs()
+            fragile &= top[..., 0] > 0
+            kidx = kw.argmax(-1)
+            self.pool_overrides += int((fragile & (kidx != idx)).sum())
+            idx = torch.where(fragile, kidx, idx)
+        return win.gather(-1, idx.unsqueeze(-1)).squeeze(-1)
 
     def __enter__(self):
         import torch.nn.functional as F
@@ -169,6 +188,11 @@ class _MaskedOracle:
             def relu(u):          # the only F.relu left is the stem's (yunet_layer.py:59-60)
                 return me._relu(u, 'stem')
 
+            @staticmethod
+            def max_pool2d(x, k):  # yunet_backbone.py:40, always right after a BN+ReLU unit
+                assert k == 2
+                return me._pool(x)
+
         orc.conv_dp_unit, orc.F = unit, FProxy()
         return self
 
@@ -185,7 +209,8 @@ def _oracle_grads(arch, img_np, gb, gl, gk, assigned, miou, dtype, masks=None):
     with _MaskedOracle(masks) as mo:
         outs = orc.model_forward(torch.from_numpy(img_np).to(dtype), Pg, Bf, arch, training=True)
     if masks is not None:
-        print(f'   oracle({dtype}): {mo.overrides} ReLU decisions of {mo.total} taken from the kernels')
+        print(f'   oracle({dtype}): {mo.overrides} ReLU and {mo.pool_overrides} max-pool decisions of '
+              f'{mo.total} taken from the kernels')
     orig = orc.simota_assign
     it = iter(range(len(gb)))
 
