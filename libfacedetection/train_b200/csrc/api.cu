@@ -304,7 +304,7 @@ int yunet_forward(yunet_ctx* ctx, const float* img, const float* params, float* 
     a.B = B; a.Hin = H; a.Win = W;
     {
       Scope sc(ctx, s, "fwd:stem", 4.0 * B * (3.0 * H * W + 16.0 * (H / 2) * (W / 2)));
-      e = launch_stem_fwd(a, s);
+      e = launch_stem_fwd(a, ctx->num_sms, s);
     }
     if (e != cudaSuccess) return cuda_fail(ctx, e, "forward: stem");
   }
@@ -335,8 +335,8 @@ int yunet_forward(yunet_ctx* ctx, const float* img, const float* params, float* 
       if (u.mode == LOAD_UPADD) bytes += 4.0 * B * u.cin * hw / 4.0;
       const bool tc = ctx->opt_tc_forward && unit_fwd_tc_supported(u.cin, u.cout, u.mode);
       Scope sc(ctx, s, (tc ? "fwd_tc:" : "fwd:") + u.name, bytes);
-      e = tc ? launch_unit_fwd_tc(u.cout, a, ctx->num_sms, v.status(), s)
-             : launch_unit_fwd(u.cin, u.cout, u.mode, a, s);
+      e = tc ? launch_unit_fwd_tc(u.cout, u.mode, a, ctx->num_sms, v.status(), s)
+             : launch_unit_fwd(u.cin, u.cout, u.mode, a, ctx->num_sms, s);
     }
     if (e != cudaSuccess) return fail(ctx, (int)e, "forward: unit %s: %s", u.name.c_str(), cudaGetErrorString(e));
   }

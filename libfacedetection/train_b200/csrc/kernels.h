@@ -90,8 +90,9 @@ struct BnFinalizeArgs {
 };
 
 // ---- launchers (kernels_fwd.cu) ----
-cudaError_t launch_unit_fwd(int cin, int cout, int mode, const UnitFwdArgs& a, cudaStream_t s);
-cudaError_t launch_stem_fwd(const StemArgs& a, cudaStream_t s);
+cudaError_t launch_unit_fwd(int cin, int cout, int mode, const UnitFwdArgs& a, int num_sms,
+                            cudaStream_t s);
+cudaError_t launch_stem_fwd(const StemArgs& a, int num_sms, cudaStream_t s);
 cudaError_t launch_bn_update_running(const BnFinalizeArgs& a, const double* sum,
                                      const double* sumsq, float* rmean, float* rvar,
                                      float momentum, cudaStream_t s);
@@ -104,7 +105,7 @@ int unit_fwd_supported(int cin, int cout);
 
 // ---- unit_fwd_tc.cu: tcgen05 / TMEM / TMA version of the fused unit (CIN = 64, plain load) ----
 int unit_fwd_tc_supported(int cin, int cout, int mode);
-cudaError_t launch_unit_fwd_tc(int cout, const UnitFwdArgs& a, int num_sms, int* status,
+cudaError_t launch_unit_fwd_tc(int cout, int mode, const UnitFwdArgs& a, int num_sms, int* status,
                                cudaStream_t s);
 
 // ---- launchers (kernels_bwd.cu) ----

@@ -107,7 +107,7 @@ struct BwdCfg {
 };
 
 template <int CIN, int COUT, int MODE, int HAS_BN>
-__global__ void __launch_bounds__(NT, 1) unit_bwd_kernel(const UnitBwdArgs a) {
+__global__ void __launch_bounds__(NT, (CIN * COUT <= 1024) ? 2 : 1) unit_bwd_kernel(const UnitBwdArgs a) {
   using C = BwdCfg<CIN, COUT>;
   extern __shared__ float4 smem_raw[];
   float* smem = reinterpret_cast<float*>(smem_raw);
@@ -165,9 +165,6 @@ __global__ void __launch_bounds__(NT, 1) unit_bwd_kernel(const UnitBwdArgs a) {
 #pragma unroll
   for (int k = 0; k < 9; ++k) gw2[k] = f4(0.f);
   float4 gb2 = f4(0.f), gb1 = f4(0.f);
-  float4 w2r[9];
-#pragma unroll
-  for (int k = 0; k < 9; ++k) w2r[k] = lds4(sW2 + k * COUT + dq * 4);
   // GEMM3 mapping
   const int o3 = tid % C::NOUT;
   const int g3 = tid / C::NOUT;
@@ -311,6 +308,9 @@ __global__ void __launch_bounds__(NT, 1) unit_bwd_kernel(const UnitBwdArgs a) {
 
     // ---- S2: depthwise backward: dy (in place over y), dW2, db2, db1
     {
+      float4 w2r[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) w2r[k] = lds4(sW2 + k * COUT + dq * 4);
       float4 ra[3], rb[3], rc[3];
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
@@ -562,7 +562,7 @@ constexpr int ST_TH = 8, ST_TW = 32;
 constexpr int ST_IH = 2 * ST_TH + 1, ST_IW = 2 * ST_TW + 1;
 constexpr int ST_IWP = ST_IW + 2;
 
-__global__ void __launch_bounds__(256, 1) stem_bwd_kernel(const StemBwdArgs a) {
+__global__ void __launch_bounds__(256, 3) stem_bwd_kernel(const StemBwdArgs a) {
   __shared__ float sIn[3][ST_IH][ST_IWP];
   __shared__ __align__(16) float sGs[ST_TH * ST_TW][16];
   __shared__ float sCo[5][16];
@@ -587,7 +587,7 @@ __global__ void __launch_bounds__(256, 1) stem_bwd_kernel(const StemBwdArgs a) {
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 3; ++j) acc[i][j] = 0.f;
-  float bsum = 0.f;   // threads 0..15 of the bias role: channel tid
+  float bsum = 0.f;   // bias gradient partial of channel tid & 15
 
   const int tiles_x = (Wo + ST_TW - 1) / ST_TW, tiles_y = (Ho + ST_TH - 1) / ST_TH;
   const int ntiles = tiles_x * tiles_y * a.B;
@@ -598,6 +598,7 @@ __global__ void __launch_bounds__(256, 1) stem_bwd_kernel(const StemBwdArgs a) {
     const int b = t / tiles_y;
     const int ox0 = tx * ST_TW, oy0 = ty * ST_TH;
     const int ix0 = 2 * ox0 - 1, iy0 = 2 * oy0 - 1;
+#pragma unroll 4
     for (int i = tid; i < 3 * ST_IH * ST_IW; i += 256) {
       int cc = i / (ST_IH * ST_IW);
       int r = (i / ST_IW) % ST_IH;
@@ -608,7 +609,9 @@ __global__ void __launch_bounds__(256, 1) stem_bwd_kernel(const StemBwdArgs a) {
         v = __ldg(a.img + (((long long)b * 3 + cc) * a.Hin + gy) * a.Win + gx);
       sIn[cc][r][x] = v;
     }
-    for (int i = tid; i < ST_TH * ST_TW * 4; i += 256) {
+#pragma unroll
+    for (int it = 0; it < ST_TH * ST_TW * 4 / 256; ++it) {
+      const int i = tid + it * 256;
       const int pix = i / 4, q = i % 4;
       const int oy = oy0 + pix / ST_TW, ox = ox0 + pix % ST_TW;
       float4 g = f4(0.f);
@@ -635,8 +638,10 @@ __global__ void __launch_bounds__(256, 1) stem_bwd_kernel(const StemBwdArgs a) {
         acc[3][0] = fmaf(g.w, v0, acc[3][0]); acc[3][1] = fmaf(g.w, v1, acc[3][1]); acc[3][2] = fmaf(g.w, v2, acc[3][2]);
       }
     }
-    if (tid < 16) {
-      for (int p = 0; p < ST_TH * ST_TW; ++p) bsum += sGs[p][tid];
+    {
+      const int bc = tid & 15;
+#pragma unroll 4
+      for (int p = tid >> 4; p < ST_TH * ST_TW; p += 16) bsum += sGs[p][bc];
     }
     __syncthreads();
   }
@@ -647,7 +652,7 @@ __global__ void __launch_bounds__(256, 1) stem_bwd_kernel(const StemBwdArgs a) {
       for (int kx = 0; kx < 3; ++kx)
         atomicAdd(a.gw + (coq * 4 + i) * 27 + c * 9 + ky * 3 + kx, acc[i][kx]);
   }
-  if (tid < 16) atomicAdd(a.gb + tid, bsum);
+  atomicAdd(a.gb + (tid & 15), bsum);
 }
 
 __global__ void bn_param_grads_kernel(const BnFinalizeArgs a, const double* dsum,
@@ -670,7 +675,8 @@ cudaError_t launch_unit_bwd_t(const UnitBwdArgs& a, int num_sms, cudaStream_t s)
     configured = true;
   }
   const int ntiles = ((a.W + TW - 1) / TW) * ((a.H + TH - 1) / TH) * a.B;
-  int grid = num_sms < ntiles ? num_sms : ntiles;
+  const int per_sm = (CIN * COUT <= 1024) ? 2 : 1;
+  int grid = per_sm * num_sms < ntiles ? per_sm * num_sms : ntiles;
   kern<<<grid, NT, smem, s>>>(a);
   return cudaGetLastError();
 }
@@ -706,7 +712,7 @@ cudaError_t launch_unit_bwd(int cin, int cout, int mode, const UnitBwdArgs& a, i
 cudaError_t launch_stem_bwd(const StemBwdArgs& a, int num_sms, cudaStream_t s) {
   const int Ho = a.Hin / 2, Wo = a.Win / 2;
   const int ntiles = ((Wo + ST_TW - 1) / ST_TW) * ((Ho + ST_TH - 1) / ST_TH) * a.B;
-  int grid = num_sms < ntiles ? num_sms : ntiles;
+  int grid = 3 * num_sms < ntiles ? 3 * num_sms : ntiles;
   stem_bwd_kernel<<<grid, 256, 0, s>>>(a);
   return cudaGetLastError();
 }

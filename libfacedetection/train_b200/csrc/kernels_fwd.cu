@@ -78,7 +78,7 @@ struct FwdCfg {
   static constexpr int NQ = COUT / 4;                // channel quads (dw stage)
   static constexpr int RG = NT / (NQ * TW);          // row groups
   static constexpr int RPT = TH / RG;                // rows per thread
-  static constexpr int SMEM_FLOATS = R0 + CIN * COUT + 9 * COUT + 2 * COUT + 4 * CIN + NT * 8;
+  static constexpr int SMEM_FLOATS = R0 + CIN * COUT + 9 * COUT + 2 * COUT + 4 * CIN;
   static_assert(HPP % NPG == 0, "pixel blocking");
   static_assert(NQ * TW * RG == NT && RG * RPT == TH, "dw mapping");
 };
@@ -98,18 +98,13 @@ __global__ void __launch_bounds__(NT, 2) unit_fwd_kernel(const UnitFwdArgs a) {
   float* sShA = sScA + CIN;
   float* sScB = sShA + CIN;
   float* sShB = sScB + CIN;
-  float* sRed = sShB + CIN;               // [NT][8]
 
   const int tid = threadIdx.x;
   const int tiles_x = (a.W + TW - 1) / TW;
   const int tiles_y = (a.H + TH - 1) / TH;
-  int t = blockIdx.x;
-  const int tx = t % tiles_x; t /= tiles_x;
-  const int ty = t % tiles_y;
-  const int b = t / tiles_y;
-  const int x0 = tx * TW, y0 = ty * TH;
+  const int ntiles = tiles_x * tiles_y * a.B;
 
-  // ---- stage 0: weights + BN coefficients into shared memory
+  // ---- stage 0 (once per persistent CTA): weights + BN coefficients into shared memory
 #pragma unroll
   for (int it = 0; it < CIN * COUT / NT; ++it) {
     const int i = tid + it * NT;
@@ -131,6 +126,19 @@ __global__ void __launch_bounds__(NT, 2) unit_fwd_kernel(const UnitFwdArgs a) {
     }
   }
   __syncthreads();
+
+  // depthwise-stage mapping, weights in registers, BatchNorm statistics accumulated over all tiles
+  const int dq = tid % C::NQ;
+  const int dx = (tid / C::NQ) % TW;
+  const int dr0 = (tid / (C::NQ * TW)) * C::RPT;
+  double st1[4] = {0.0, 0.0, 0.0, 0.0}, st2[4] = {0.0, 0.0, 0.0, 0.0};
+
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  int t = tile;
+  const int tx = t % tiles_x; t /= tiles_x;
+  const int ty = t % tiles_y;
+  const int b = t / tiles_y;
+  const int x0 = tx * TW, y0 = ty * TH;
 
   // ---- stage 1: halo tile of activated inputs -> sA
   {
@@ -233,27 +241,23 @@ __global__ void __launch_bounds__(NT, 2) unit_fwd_kernel(const UnitFwdArgs a) {
 
   // ---- stage 3: depthwise 3x3 from shared memory, store z, statistics
   {
-    const int q = tid % C::NQ;
-    const int x = (tid / C::NQ) % TW;
-    const int rg = tid / (C::NQ * TW);
-    const int r0 = rg * C::RPT;
     float4 w[9];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) w[k] = *reinterpret_cast<const float4*>(sW2 + k * COUT + q * 4);
-    const float4 bias = *reinterpret_cast<const float4*>(sB2 + q * 4);
+    for (int k = 0; k < 9; ++k) w[k] = *reinterpret_cast<const float4*>(sW2 + k * COUT + dq * 4);
+    const float4 bias = *reinterpret_cast<const float4*>(sB2 + dq * 4);
     float4 ra[3], rb[3], rc[3];
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-      ra[d] = *reinterpret_cast<const float4*>(sY + ((r0 + 0) * HW + x + d) * COUT + q * 4);
-      rb[d] = *reinterpret_cast<const float4*>(sY + ((r0 + 1) * HW + x + d) * COUT + q * 4);
+      ra[d] = *reinterpret_cast<const float4*>(sY + ((dr0 + 0) * HW + dx + d) * COUT + dq * 4);
+      rb[d] = *reinterpret_cast<const float4*>(sY + ((dr0 + 1) * HW + dx + d) * COUT + dq * 4);
     }
     float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
-    const int gx = x0 + x;
+    const int gx = x0 + dx;
 #pragma unroll
     for (int i = 0; i < C::RPT; ++i) {
 #pragma unroll
       for (int d = 0; d < 3; ++d)
-        rc[d] = *reinterpret_cast<const float4*>(sY + ((r0 + i + 2) * HW + x + d) * COUT + q * 4);
+        rc[d] = *reinterpret_cast<const float4*>(sY + ((dr0 + i + 2) * HW + dx + d) * COUT + dq * 4);
       float4 o = bias;
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
@@ -261,9 +265,9 @@ __global__ void __launch_bounds__(NT, 2) unit_fwd_kernel(const UnitFwdArgs a) {
         fma4(o, w[3 + d], rb[d]);
         fma4(o, w[6 + d], rc[d]);
       }
-      const int gy = y0 + r0 + i;
+      const int gy = y0 + dr0 + i;
       if (gy < a.H && gx < a.W) {
-        float* dst = a.zout + (long long)b * a.out_batch_stride + ((long long)gy * a.W + gx) * COUT + q * 4;
+        float* dst = a.zout + (long long)b * a.out_batch_stride + ((long long)gy * a.W + gx) * COUT + dq * 4;
         *reinterpret_cast<float4*>(dst) = o;
         s1 = add4(s1, o);
         s2.x = fmaf(o.x, o.x, s2.x); s2.y = fmaf(o.y, o.y, s2.y);
@@ -272,107 +276,143 @@ __global__ void __launch_bounds__(NT, 2) unit_fwd_kernel(const UnitFwdArgs a) {
 #pragma unroll
       for (int d = 0; d < 3; ++d) { ra[d] = rb[d]; rb[d] = rc[d]; }
     }
-    if (a.osum != nullptr) {
-      *reinterpret_cast<float4*>(sRed + tid * 8) = s1;
-      *reinterpret_cast<float4*>(sRed + tid * 8 + 4) = s2;
-    }
+    st1[0] += s1.x; st1[1] += s1.y; st1[2] += s1.z; st1[3] += s1.w;
+    st2[0] += s2.x; st2[1] += s2.y; st2[2] += s2.z; st2[3] += s2.w;
   }
+  __syncthreads();   // sY is overwritten (as sA) by the next tile
+  }  // tile loop
+
+  // ---- statistics: fp32 within a tile row-strip, fp64 across tiles / lanes / CTAs
   if (a.osum != nullptr) {
-    __syncthreads();
-    if (tid < 2 * COUT) {
-      const int c = tid % COUT, which = tid / COUT;
-      const int q = c / 4, lane = c % 4;
-      double s = 0.0;
-      for (int th = q; th < NT; th += C::NQ) s += (double)sRed[th * 8 + which * 4 + lane];
-      atomicAdd((which == 0 ? a.osum : a.osumsq) + c, s);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+#pragma unroll
+      for (int o = 16; o >= C::NQ; o >>= 1) {
+        st1[c] += __shfl_xor_sync(0xffffffffu, st1[c], o);
+        st2[c] += __shfl_xor_sync(0xffffffffu, st2[c], o);
+      }
+    }
+    if ((tid & 31) < C::NQ) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        atomicAdd(a.osum + dq * 4 + c, st1[c]);
+        atomicAdd(a.osumsq + dq * 4 + c, st2[c]);
+      }
     }
   }
 }
 
 // ------------------------------------------------------------------------------- stem
-constexpr int ST_TH = 8, ST_TW = 32;
-constexpr int ST_IH = 2 * ST_TH + 1, ST_IW = 2 * ST_TW + 1;   // 17 x 65 input patch
-constexpr int ST_IWP = ST_IW + 2;                             // row stride 67 (odd: fewer conflicts)
+// Persistent CTAs; tile = 16 rows x 32 cols of output pixels, 2 pixels (rows ly, ly+8) per thread
+// so every broadcast weight load feeds two pixels; per-lane fp64 statistics across tiles.
+constexpr int ST_TH = 16, ST_TW = 32;
+constexpr int ST_IH = 2 * ST_TH + 1, ST_IW = 2 * ST_TW + 1;   // 33 x 65 input patch
+constexpr int ST_IWP = ST_IW + 2;                             // row stride 67
 
-__global__ void __launch_bounds__(256) stem_fwd_kernel(const StemArgs a) {
+__global__ void __launch_bounds__(256, 2) stem_fwd_kernel(const StemArgs a) {
   __shared__ float sIn[3][ST_IH][ST_IWP];
   __shared__ __align__(16) float sW[27][16];
   __shared__ float sB[16];
-  __shared__ float sRed[8][32];
-  const int tid = threadIdx.x;
+  __shared__ double sRedD[8][32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int Ho = a.Hin / 2, Wo = a.Win / 2;
   const int tiles_x = (Wo + ST_TW - 1) / ST_TW, tiles_y = (Ho + ST_TH - 1) / ST_TH;
-  int t = blockIdx.x;
-  const int tx = t % tiles_x; t /= tiles_x;
-  const int ty = t % tiles_y;
-  const int b = t / tiles_y;
-  const int ox0 = tx * ST_TW, oy0 = ty * ST_TH;
-  const int ix0 = 2 * ox0 - 1, iy0 = 2 * oy0 - 1;
-
+  const int ntiles = tiles_x * tiles_y * a.B;
   for (int i = tid; i < 27 * 16; i += 256) {
     int k = i / 16, co = i % 16;
     sW[k][co] = __ldg(a.w + co * 27 + k);
   }
   if (tid < 16) sB[tid] = __ldg(a.b + tid);
-  for (int i = tid; i < 3 * ST_IH * ST_IW; i += 256) {
-    int c = i / (ST_IH * ST_IW);
-    int r = (i / ST_IW) % ST_IH;
-    int x = i % ST_IW;
-    int gy = iy0 + r, gx = ix0 + x;
-    float v = 0.f;
-    if (gy >= 0 && gy < a.Hin && gx >= 0 && gx < a.Win)
-      v = __ldg(a.img + (((long long)b * 3 + c) * a.Hin + gy) * a.Win + gx);
-    sIn[c][r][x] = v;
-  }
-  __syncthreads();
+  const int lx = tid % ST_TW, ly = tid / ST_TW;    // ly in 0..7; second pixel at ly + 8
+  double stat = 0.0;    // lane L: sum of channel L (L < 16) / sum of squares of channel L-16
 
-  const int lx = tid % ST_TW, ly = tid / ST_TW;
-  float acc[16];
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    int t = tile;
+    const int tx = t % tiles_x; t /= tiles_x;
+    const int ty = t % tiles_y;
+    const int b = t / tiles_y;
+    const int ox0 = tx * ST_TW, oy0 = ty * ST_TH;
+    const int ix0 = 2 * ox0 - 1, iy0 = 2 * oy0 - 1;
+    __syncthreads();      // previous tile's readers of sIn are done (also covers the weight setup)
+#pragma unroll 4
+    for (int i = tid; i < 3 * ST_IH * ST_IW; i += 256) {
+      int c = i / (ST_IH * ST_IW);
+      int r = (i / ST_IW) % ST_IH;
+      int x = i % ST_IW;
+      int gy = iy0 + r, gx = ix0 + x;
+      float v = 0.f;
+      if (gy >= 0 && gy < a.Hin && gx >= 0 && gx < a.Win)
+        v = __ldg(a.img + (((long long)b * 3 + c) * a.Hin + gy) * a.Win + gx);
+      sIn[c][r][x] = v;
+    }
+    __syncthreads();
+
+    float acc[2][16];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) acc[j] = sB[j];
+    for (int j = 0; j < 16; ++j) { acc[0][j] = sB[j]; acc[1][j] = sB[j]; }
 #pragma unroll
-  for (int c = 0; c < 3; ++c)
+    for (int c = 0; c < 3; ++c)
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky)
+      for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const float v = sIn[c][2 * ly + ky][2 * lx + kx];
-        const int k = c * 9 + ky * 3 + kx;
+        for (int kx = 0; kx < 3; ++kx) {
+          const float v0 = sIn[c][2 * ly + ky][2 * lx + kx];
+          const float v1 = sIn[c][2 * (ly + 8) + ky][2 * lx + kx];
+          const int k = c * 9 + ky * 3 + kx;
 #pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) {
-          const float4 w = *reinterpret_cast<const float4*>(&sW[k][j4 * 4]);
-          acc[j4 * 4 + 0] = fmaf(v, w.x, acc[j4 * 4 + 0]);
-          acc[j4 * 4 + 1] = fmaf(v, w.y, acc[j4 * 4 + 1]);
-          acc[j4 * 4 + 2] = fmaf(v, w.z, acc[j4 * 4 + 2]);
-          acc[j4 * 4 + 3] = fmaf(v, w.w, acc[j4 * 4 + 3]);
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 w = *reinterpret_cast<const float4*>(&sW[k][j4 * 4]);
+            acc[0][j4 * 4 + 0] = fmaf(v0, w.x, acc[0][j4 * 4 + 0]);
+            acc[0][j4 * 4 + 1] = fmaf(v0, w.y, acc[0][j4 * 4 + 1]);
+            acc[0][j4 * 4 + 2] = fmaf(v0, w.z, acc[0][j4 * 4 + 2]);
+            acc[0][j4 * 4 + 3] = fmaf(v0, w.w, acc[0][j4 * 4 + 3]);
+            acc[1][j4 * 4 + 0] = fmaf(v1, w.x, acc[1][j4 * 4 + 0]);
+            acc[1][j4 * 4 + 1] = fmaf(v1, w.y, acc[1][j4 * 4 + 1]);
+            acc[1][j4 * 4 + 2] = fmaf(v1, w.z, acc[1][j4 * 4 + 2]);
+            acc[1][j4 * 4 + 3] = fmaf(v1, w.w, acc[1][j4 * 4 + 3]);
+          }
+        }
+    float vals[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) vals[j] = 0.f;
+    const int ox = ox0 + lx;
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      const int oy = oy0 + ly + p * 8;
+      if (oy < Ho && ox < Wo) {
+        float* dst = a.zout + (((long long)b * Ho + oy) * Wo + ox) * 16;
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4)
+          *reinterpret_cast<float4*>(dst + j4 * 4) =
+              make_float4(acc[p][j4 * 4], acc[p][j4 * 4 + 1], acc[p][j4 * 4 + 2], acc[p][j4 * 4 + 3]);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          vals[j] += acc[p][j];
+          vals[16 + j] = fmaf(acc[p][j], acc[p][j], vals[16 + j]);
         }
       }
-  const int oy = oy0 + ly, ox = ox0 + lx;
-  const bool valid = oy < Ho && ox < Wo;
-  if (valid) {
-    float* dst = a.zout + (((long long)b * Ho + oy) * Wo + ox) * 16;
+    }
+    if (a.osum != nullptr) {
+      // butterfly transpose-reduce: 31 shuffles leave the warp total of value index L on lane L
 #pragma unroll
-    for (int j4 = 0; j4 < 4; ++j4)
-      *reinterpret_cast<float4*>(dst + j4 * 4) =
-          make_float4(acc[j4 * 4], acc[j4 * 4 + 1], acc[j4 * 4 + 2], acc[j4 * 4 + 3]);
+      for (int s = 16; s >= 1; s >>= 1) {
+        const bool upper = (lane & s) != 0;
+#pragma unroll
+        for (int i = 0; i < s; ++i) {
+          const float send = upper ? vals[i] : vals[i + s];
+          const float keep = upper ? vals[i + s] : vals[i];
+          vals[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+      }
+      stat += (double)vals[0];
+    }
   }
   if (a.osum != nullptr) {
-    const int lane = tid & 31, warp = tid >> 5;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      float s1 = valid ? acc[j] : 0.f;
-      float s2 = valid ? acc[j] * acc[j] : 0.f;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-      }
-      if (lane == 0) { sRed[warp][j] = s1; sRed[warp][16 + j] = s2; }
-    }
+    sRedD[warp][lane] = stat;
     __syncthreads();
     if (tid < 32) {
       double s = 0.0;
-      for (int w = 0; w < 8; ++w) s += (double)sRed[w][tid];
+      for (int w = 0; w < 8; ++w) s += sRedD[w][tid];
       atomicAdd((tid < 16 ? a.osum : a.osumsq) + (tid & 15), s);
     }
   }
@@ -430,7 +470,7 @@ __global__ void grid_priors_kernel(float* priors, int h0, int w0, int s0, int h1
 }
 
 template <int CIN, int COUT, int MODE>
-cudaError_t launch_unit_fwd_t(const UnitFwdArgs& a, cudaStream_t s) {
+cudaError_t launch_unit_fwd_t(const UnitFwdArgs& a, int num_sms, cudaStream_t s) {
   using C = FwdCfg<CIN, COUT>;
   const size_t smem = sizeof(float) * C::SMEM_FLOATS;
   auto kern = unit_fwd_kernel<CIN, COUT, MODE>;
@@ -440,17 +480,19 @@ cudaError_t launch_unit_fwd_t(const UnitFwdArgs& a, cudaStream_t s) {
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  const int tiles = ((a.W + TW - 1) / TW) * ((a.H + TH - 1) / TH);
-  kern<<<tiles * a.B, NT, smem, s>>>(a);
+  const int tiles = ((a.W + TW - 1) / TW) * ((a.H + TH - 1) / TH) * a.B;
+  int grid = 2 * num_sms;            // persistent: __launch_bounds__(NT, 2)
+  if (grid > tiles) grid = tiles;
+  kern<<<grid, NT, smem, s>>>(a);
   return cudaGetLastError();
 }
 
 template <int CIN, int COUT>
-cudaError_t launch_unit_fwd_m(int mode, const UnitFwdArgs& a, cudaStream_t s) {
+cudaError_t launch_unit_fwd_m(int mode, const UnitFwdArgs& a, int num_sms, cudaStream_t s) {
   switch (mode) {
-    case 0: return launch_unit_fwd_t<CIN, COUT, 0>(a, s);
-    case 1: return launch_unit_fwd_t<CIN, COUT, 1>(a, s);
-    case 2: return launch_unit_fwd_t<CIN, COUT, 2>(a, s);
+    case 0: return launch_unit_fwd_t<CIN, COUT, 0>(a, num_sms, s);
+    case 1: return launch_unit_fwd_t<CIN, COUT, 1>(a, num_sms, s);
+    case 2: return launch_unit_fwd_t<CIN, COUT, 2>(a, num_sms, s);
   }
   return cudaErrorInvalidValue;
 }
@@ -462,21 +504,24 @@ int unit_fwd_supported(int cin, int cout) {
          (cin == 32 && (cout == 32 || cout == 64)) || (cin == 64 && (cout == 64 || cout == 16));
 }
 
-cudaError_t launch_unit_fwd(int cin, int cout, int mode, const UnitFwdArgs& a, cudaStream_t s) {
-  if (cin == 16 && cout == 16) return launch_unit_fwd_m<16, 16>(mode, a, s);
-  if (cin == 16 && cout == 32) return launch_unit_fwd_m<16, 32>(mode, a, s);
-  if (cin == 16 && cout == 64) return launch_unit_fwd_m<16, 64>(mode, a, s);
-  if (cin == 32 && cout == 32) return launch_unit_fwd_m<32, 32>(mode, a, s);
-  if (cin == 32 && cout == 64) return launch_unit_fwd_m<32, 64>(mode, a, s);
-  if (cin == 64 && cout == 64) return launch_unit_fwd_m<64, 64>(mode, a, s);
-  if (cin == 64 && cout == 16) return launch_unit_fwd_m<64, 16>(mode, a, s);
+cudaError_t launch_unit_fwd(int cin, int cout, int mode, const UnitFwdArgs& a, int num_sms,
+                            cudaStream_t s) {
+  if (cin == 16 && cout == 16) return launch_unit_fwd_m<16, 16>(mode, a, num_sms, s);
+  if (cin == 16 && cout == 32) return launch_unit_fwd_m<16, 32>(mode, a, num_sms, s);
+  if (cin == 16 && cout == 64) return launch_unit_fwd_m<16, 64>(mode, a, num_sms, s);
+  if (cin == 32 && cout == 32) return launch_unit_fwd_m<32, 32>(mode, a, num_sms, s);
+  if (cin == 32 && cout == 64) return launch_unit_fwd_m<32, 64>(mode, a, num_sms, s);
+  if (cin == 64 && cout == 64) return launch_unit_fwd_m<64, 64>(mode, a, num_sms, s);
+  if (cin == 64 && cout == 16) return launch_unit_fwd_m<64, 16>(mode, a, num_sms, s);
   return cudaErrorInvalidValue;
 }
 
-cudaError_t launch_stem_fwd(const StemArgs& a, cudaStream_t s) {
+cudaError_t launch_stem_fwd(const StemArgs& a, int num_sms, cudaStream_t s) {
   const int Ho = a.Hin / 2, Wo = a.Win / 2;
-  const int tiles = ((Wo + ST_TW - 1) / ST_TW) * ((Ho + ST_TH - 1) / ST_TH);
-  stem_fwd_kernel<<<tiles * a.B, 256, 0, s>>>(a);
+  const int tiles = ((Wo + ST_TW - 1) / ST_TW) * ((Ho + ST_TH - 1) / ST_TH) * a.B;
+  int grid = 2 * num_sms;
+  if (grid > tiles) grid = tiles;
+  stem_fwd_kernel<<<grid, 256, 0, s>>>(a);
   return cudaGetLastError();
 }
 

@@ -15,6 +15,7 @@
 // does its epilogue while block 1's MMAs run).  CIN = 64, plain load mode (no pool / up-add).
 // Reference semantics: mmdet/models/utils/yunet_layer.py:30-36.
 #include <cstdio>
+#include <cstring>
 
 #include "kernels.h"
 #include "tc_common.cuh"
@@ -59,7 +60,9 @@ struct TcCfg {
   static constexpr uint32_t OFF_B2 = OFF_B1 + COUT * 4;
   static constexpr uint32_t OFF_SC = OFF_B2 + COUT * 4;               // [64]
   static constexpr uint32_t OFF_SH = OFF_SC + CIN * 4;
-  static constexpr uint32_t OFF_BAR = OFF_SH + CIN * 4;               // 3 mbarriers + tmem ptr
+  static constexpr uint32_t OFF_SCB = OFF_SH + CIN * 4;               // up-add operand b
+  static constexpr uint32_t OFF_SHB = OFF_SCB + CIN * 4;
+  static constexpr uint32_t OFF_BAR = OFF_SHB + CIN * 4;              // 3 mbarriers + tmem ptr
   static constexpr uint32_t SMEM = OFF_BAR + 64;
   static constexpr int NQ = COUT / 4;
   static constexpr int RGN = NT / (NQ * 16);
@@ -75,7 +78,7 @@ __device__ __forceinline__ float* y_chunk(unsigned char* base, int pix, int chun
   return reinterpret_cast<float*>(base + pix * ROWB + ((chunk ^ (pix & MASK)) << 4));
 }
 
-template <int COUT>
+template <int COUT, int MODE>
 __global__ void __launch_bounds__(NT, 2)
 unit_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const UnitFwdArgs a, int* status) {
   using C = TcCfg<COUT>;
@@ -90,6 +93,8 @@ unit_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const UnitFwdArgs a
   float* sB2 = reinterpret_cast<float*>(smem + C::OFF_B2);
   float* sSc = reinterpret_cast<float*>(smem + C::OFF_SC);
   float* sSh = reinterpret_cast<float*>(smem + C::OFF_SH);
+  float* sScB = reinterpret_cast<float*>(smem + C::OFF_SCB);
+  float* sShB = reinterpret_cast<float*>(smem + C::OFF_SHB);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);   // [0] tma, [1] mma0, [2] mma1
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3);
 
@@ -122,6 +127,10 @@ unit_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const UnitFwdArgs a
     float sc, sh;
     bn_coeffs_tc(a.bna, tid, sc, sh);
     sSc[tid] = sc; sSh[tid] = sh;
+    if (MODE == 2) {
+      bn_coeffs_tc(a.bnb, tid, sc, sh);
+      sScB[tid] = sc; sShB[tid] = sh;
+    }
   }
   fence_proxy_async_smem();
   tc_fence_before();
@@ -155,16 +164,60 @@ unit_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const UnitFwdArgs a
     const int b = t / tiles_y;
     const int x0 = tx * OT, y0 = ty * OT;
 
-    // ---- TMA: 4 boxes of (32 ch, 16 cols, 8 rows, 1 image) = 16 KB each
-    if (tid == 0) {
-      mbar_arrive_expect_tx(&bars[0], RAW_BYTES);
+    if (MODE == 0) {
+      // ---- TMA: 4 boxes of (32 ch, 16 cols, 8 rows, 1 image) = 16 KB each
+      if (tid == 0) {
+        mbar_arrive_expect_tx(&bars[0], RAW_BYTES);
 #pragma unroll
-      for (int m = 0; m < 2; ++m)
+        for (int m = 0; m < 2; ++m)
 #pragma unroll
-        for (int kb = 0; kb < 2; ++kb)
-          tma_load_4d(raw + (m * 2 + kb) * 16384, &tmap, &bars[0], kb * 32, x0 - 1, y0 - 1 + m * 8, b);
+          for (int kb = 0; kb < 2; ++kb)
+            tma_load_4d(raw + (m * 2 + kb) * 16384, &tmap, &bars[0], kb * 32, x0 - 1, y0 - 1 + m * 8, b);
+      }
+      if (!mbar_wait(&bars[0], ph)) { alive = false; if (lane == 0) atomicExch(status, 1); }
+    } else {
+      // ---- pooled / up-added operand: cooperative vector loads, activation applied on the way,
+      // written in the layout the TMA would have produced (row = pixel, 16 B chunks ^ (row & 7))
+#pragma unroll 4
+      for (int it = 0; it < HPIX * 16 / NT; ++it) {
+        const int i = tid + it * NT;
+        const int pix = i >> 4, ch = i & 15;
+        const int gy = y0 - 1 + pix / HT, gx = x0 - 1 + pix % HT;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) {
+          const float4 sc = *reinterpret_cast<const float4*>(sSc + ch * 4);
+          const float4 sh = *reinterpret_cast<const float4*>(sSh + ch * 4);
+          if (MODE == 1) {
+            const int W2 = a.W * 2;
+            const float* p = a.za + (((long long)b * (a.H * 2) + gy * 2) * W2 + gx * 2) * CIN + ch * 4;
+            const float4 z00 = __ldg(reinterpret_cast<const float4*>(p));
+            const float4 z01 = __ldg(reinterpret_cast<const float4*>(p + CIN));
+            const float4 z10 = __ldg(reinterpret_cast<const float4*>(p + (long long)W2 * CIN));
+            const float4 z11 = __ldg(reinterpret_cast<const float4*>(p + (long long)W2 * CIN + CIN));
+            v.x = fmaxf(fmaxf(fmaxf(fmaf(z00.x, sc.x, sh.x), fmaf(z01.x, sc.x, sh.x)), fmaxf(fmaf(z10.x, sc.x, sh.x), fmaf(z11.x, sc.x, sh.x))), 0.f);
+            v.y = fmaxf(fmaxf(fmaxf(fmaf(z00.y, sc.y, sh.y), fmaf(z01.y, sc.y, sh.y)), fmaxf(fmaf(z10.y, sc.y, sh.y), fmaf(z11.y, sc.y, sh.y))), 0.f);
+            v.z = fmaxf(fmaxf(fmaxf(fmaf(z00.z, sc.z, sh.z), fmaf(z01.z, sc.z, sh.z)), fmaxf(fmaf(z10.z, sc.z, sh.z), fmaf(z11.z, sc.z, sh.z))), 0.f);
+            v.w = fmaxf(fmaxf(fmaxf(fmaf(z00.w, sc.w, sh.w), fmaf(z01.w, sc.w, sh.w)), fmaxf(fmaf(z10.w, sc.w, sh.w), fmaf(z11.w, sc.w, sh.w))), 0.f);
+          } else {
+            const float* p = a.za + (((long long)b * a.H + gy) * a.W + gx) * CIN + ch * 4;
+            const float4 z = __ldg(reinterpret_cast<const float4*>(p));
+            const int Hb = a.H >> 1, Wb = a.W >> 1;
+            const float* pb = a.zb + (((long long)b * Hb + (gy >> 1)) * Wb + (gx >> 1)) * CIN + ch * 4;
+            const float4 zb = __ldg(reinterpret_cast<const float4*>(pb));
+            const float4 scb = *reinterpret_cast<const float4*>(sScB + ch * 4);
+            const float4 shb = *reinterpret_cast<const float4*>(sShB + ch * 4);
+            v.x = fmaxf(fmaf(z.x, sc.x, sh.x), 0.f) + fmaxf(fmaf(zb.x, scb.x, shb.x), 0.f);
+            v.y = fmaxf(fmaf(z.y, sc.y, sh.y), 0.f) + fmaxf(fmaf(zb.y, scb.y, shb.y), 0.f);
+            v.z = fmaxf(fmaf(z.z, sc.z, sh.z), 0.f) + fmaxf(fmaf(zb.z, scb.z, shb.z), 0.f);
+            v.w = fmaxf(fmaf(z.w, sc.w, sh.w), 0.f) + fmaxf(fmaf(zb.w, scb.w, shb.w), 0.f);
+          }
+        }
+        const int r = pix & 127;
+        *reinterpret_cast<float4*>(raw + ((pix >> 7) * 2 + (ch >> 3)) * 16384 + r * 128 +
+                                   (((ch & 7) ^ (r & 7)) << 4)) = v;
+      }
+      __syncthreads();
     }
-    if (!mbar_wait(&bars[0], ph)) { alive = false; if (lane == 0) atomicExch(status, 1); }
 
     // ---- conversion of M block `mblk`: block 1 first waits until block 0's MMAs released the
     // shared A columns of TMEM
@@ -185,8 +238,11 @@ unit_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const UnitFwdArgs a
           const float4 z = *reinterpret_cast<const float4*>(rowp + kb * 16384 + ((cc ^ (r & 7)) << 4));
           const float4 sc = *reinterpret_cast<const float4*>(sSc + c * 4);
           const float4 sh = *reinterpret_cast<const float4*>(sSh + c * 4);
-          const float v0 = fmaxf(fmaf(z.x, sc.x, sh.x), 0.f), v1 = fmaxf(fmaf(z.y, sc.y, sh.y), 0.f);
-          const float v2 = fmaxf(fmaf(z.z, sc.z, sh.z), 0.f), v3 = fmaxf(fmaf(z.w, sc.w, sh.w), 0.f);
+          float v0 = z.x, v1 = z.y, v2 = z.z, v3 = z.w;     // MODE 1/2: already activated
+          if (MODE == 0) {
+            v0 = fmaxf(fmaf(z.x, sc.x, sh.x), 0.f); v1 = fmaxf(fmaf(z.y, sc.y, sh.y), 0.f);
+            v2 = fmaxf(fmaf(z.z, sc.z, sh.z), 0.f); v3 = fmaxf(fmaf(z.w, sc.w, sh.w), 0.f);
+          }
           hi[c4 * 4 + 0] = tf32_hi(v0); lo[c4 * 4 + 0] = tf32_lo(v0);
           hi[c4 * 4 + 1] = tf32_hi(v1); lo[c4 * 4 + 1] = tf32_lo(v1);
           hi[c4 * 4 + 2] = tf32_hi(v2); lo[c4 * 4 + 2] = tf32_lo(v2);
@@ -333,12 +389,12 @@ EncodeFn get_encode() {
   return fn;
 }
 
-template <int COUT>
+template <int COUT, int MODE>
 cudaError_t launch_tc_t(const CUtensorMap& tm, const UnitFwdArgs& a, int num_sms, int* status,
                         cudaStream_t s) {
   using C = TcCfg<COUT>;
   const size_t smem = C::SMEM + 1024;
-  auto kern = unit_fwd_tc_kernel<COUT>;
+  auto kern = unit_fwd_tc_kernel<COUT, MODE>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -355,27 +411,34 @@ cudaError_t launch_tc_t(const CUtensorMap& tm, const UnitFwdArgs& a, int num_sms
 }  // namespace
 
 int unit_fwd_tc_supported(int cin, int cout, int mode) {
-  return cin == 64 && mode == 0 && (cout == 64 || cout == 16) && get_encode() != nullptr;
+  if (cin != 64 || get_encode() == nullptr) return 0;
+  if (cout == 64) return mode >= 0 && mode <= 2;
+  return cout == 16 && mode == 0;
 }
 
 // `status`: device int, set non-zero if a bounded wait inside the kernel timed out.
-cudaError_t launch_unit_fwd_tc(int cout, const UnitFwdArgs& a, int num_sms, int* status,
+cudaError_t launch_unit_fwd_tc(int cout, int mode, const UnitFwdArgs& a, int num_sms, int* status,
                                cudaStream_t s) {
   EncodeFn enc = get_encode();
   if (!enc) return cudaErrorNotSupported;
   CUtensorMap tm;
-  // NHWC input as a 4-D tensor (C, W, H, B); box = 32 channels x 16 cols x 8 rows x 1 image
-  cuuint64_t dims[4] = {(cuuint64_t)CIN, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.B};
-  cuuint64_t strides[3] = {(cuuint64_t)CIN * 4, (cuuint64_t)a.W * CIN * 4,
-                           (cuuint64_t)a.H * a.W * CIN * 4};
-  cuuint32_t box[4] = {32, HT, 8, 1};
-  cuuint32_t es[4] = {1, 1, 1, 1};
-  CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(a.za), dims, strides,
-                   box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
-  if (cout == 64) return launch_tc_t<64>(tm, a, num_sms, status, s);
-  if (cout == 16) return launch_tc_t<16>(tm, a, num_sms, status, s);
+  memset(&tm, 0, sizeof tm);
+  if (mode == 0) {
+    // NHWC input as a 4-D tensor (C, W, H, B); box = 32 channels x 16 cols x 8 rows x 1 image
+    cuuint64_t dims[4] = {(cuuint64_t)CIN, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.B};
+    cuuint64_t strides[3] = {(cuuint64_t)CIN * 4, (cuuint64_t)a.W * CIN * 4,
+                             (cuuint64_t)a.H * a.W * CIN * 4};
+    cuuint32_t box[4] = {32, HT, 8, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(a.za), dims, strides,
+                     box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+  }
+  if (cout == 64 && mode == 0) return launch_tc_t<64, 0>(tm, a, num_sms, status, s);
+  if (cout == 64 && mode == 1) return launch_tc_t<64, 1>(tm, a, num_sms, status, s);
+  if (cout == 64 && mode == 2) return launch_tc_t<64, 2>(tm, a, num_sms, status, s);
+  if (cout == 16 && mode == 0) return launch_tc_t<16, 0>(tm, a, num_sms, status, s);
   return cudaErrorInvalidValue;
 }
 

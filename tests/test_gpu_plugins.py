@@ -80,7 +80,9 @@ def test_train_step_through_autograd_and_torch_sgd(arch, seed):
     opt.step()
     sd = m.state_dict()
     for k, _ in m.named_parameters():
-        assert _rel(sd[k], g['after/' + k]) < 1e-3, k
+        ref = torch.from_numpy(g['after/' + k])
+        err = float((sd[k].cpu() - ref).abs().max())
+        assert err <= 1e-3 * float(ref.abs().max()) + 5e-6 * gmax, (k, err)
     for k in sd:
         if 'running_' in k:
             assert _rel(sd[k], g['after/' + k]) < 1e-3, k
