@@ -195,9 +195,10 @@ int yunet_read_activation(yunet_ctx* ctx, int unit_index, const float* params,
  * number of records, yunet_profile_get returns name ("fwd:<unit>", "bwd:<unit>", ...), duration
  * and the algorithmic bytes of record i. */
 long long yunet_launch_count(const yunet_ctx* ctx);
-/* options: "tc_forward" = 1 runs the 64-channel plain-load units through the tcgen05/TMEM/TMA
- * kernel (3xTF32, fp32-accurate); device-side bounded waits report into the status block
- * (yunet_ws_offset kind 3: int[64], all zero = ok). */
+/* options (default 1): "tc_forward" runs the 64-input-channel units, "tc_backward" the 64->64
+ * plain-load unit backward through the tcgen05/TMEM/TMA kernels (3xTF32, fp32-accurate); 0 selects
+ * the exact-fp32 CUDA-core kernels.  Device-side bounded waits report into the status block
+ * (yunet_ws_offset kind 3: int[64], [0] forward, [1] backward; all zero = ok). */
 int yunet_set_option(yunet_ctx* ctx, const char* name, int value);
 /* byte offset inside the workspace of tensor `tensor_id`'s pre-BN activation (kind 0), its
  * activation gradient (kind 1, train only) or the BatchNorm statistics block (kind 2: double

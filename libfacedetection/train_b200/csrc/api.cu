@@ -26,6 +26,7 @@ struct yunet_ctx {
   bool sms_known = false;
   long long launches = 0;       // kernels launched by this ctx (bench.py's gpu_launches)
   int opt_tc_forward = 1;       // use the tcgen05 unit kernel where it applies (default on)
+  int opt_tc_backward = 1;      // same for the unit backward (64->64 plain units)
   bool profiling = false;
   std::vector<ProfEvent> prof;
   std::vector<float> prof_ms;
@@ -425,6 +426,8 @@ int yunet_backward(yunet_ctx* ctx, const float* img, const float* params, const 
   if (e != cudaSuccess) return cuda_fail(ctx, e, "backward: memset grads");
   e = cudaMemsetAsync(v.stat(2), 0, sizeof(double) * 2 * (size_t)p.num_bn_ch, s);
   if (e != cudaSuccess) return cuda_fail(ctx, e, "backward: memset statistics");
+  e = cudaMemsetAsync(v.status() + 1, 0, sizeof(int), s);
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "backward: memset status");
   for (int i = (int)p.units.size() - 1; i >= 0; --i) {
     const UnitDesc& u = p.units[i];
     UnitBwdArgs a;
@@ -469,8 +472,10 @@ int yunet_backward(yunet_ctx* ctx, const float* img, const float* params, const 
       double bytes = 4.0 * B * (2.0 * u.cin * hw * (u.mode == LOAD_POOL ? 4.0 : 1.0) +
                                 (u.has_bn ? 2.0 : 1.0) * u.cout * hw);
       if (u.mode == LOAD_UPADD) bytes += 4.0 * B * 2.0 * u.cin * hw / 4.0;
-      Scope sc(ctx, s, "bwd:" + u.name, bytes);
-      e = launch_unit_bwd(u.cin, u.cout, u.mode, a, ctx->num_sms, s);
+      const bool tc = ctx->opt_tc_backward && unit_bwd_tc_supported(u.cin, u.cout, u.mode, a.has_bn);
+      Scope sc(ctx, s, (tc ? "bwd_tc:" : "bwd:") + u.name, bytes);
+      e = tc ? launch_unit_bwd_tc(a, ctx->num_sms, v.status() + 1, s)
+             : launch_unit_bwd(u.cin, u.cout, u.mode, a, ctx->num_sms, s);
     }
     if (e != cudaSuccess) return fail(ctx, (int)e, "backward: unit %s: %s", u.name.c_str(), cudaGetErrorString(e));
   }
@@ -526,6 +531,7 @@ long long yunet_launch_count(const yunet_ctx* ctx) { return ctx ? ctx->launches 
 int yunet_set_option(yunet_ctx* ctx, const char* name, int value) {
   if (!ctx || !name) return -1;
   if (strcmp(name, "tc_forward") == 0) { ctx->opt_tc_forward = value ? 1 : 0; return 0; }
+  if (strcmp(name, "tc_backward") == 0) { ctx->opt_tc_backward = value ? 1 : 0; return 0; }
   return fail(ctx, -1, "unknown option %s", name);
 }
 

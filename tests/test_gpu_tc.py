@@ -66,3 +66,33 @@ def test_tc_forward_matches_reference_golden():
     e = _rel(preds, torch.from_numpy(g['preds']))
     print(f'tc forward vs reference golden (640): {e:.3e}')
     assert e < 1e-3
+
+
+@pytest.mark.parametrize('arch', ['yunet_n', 'yunet_s'])
+@pytest.mark.parametrize('shape', [(3, 96, 160), (2, 320, 320)])
+def test_tc_backward_equals_fp32_path(arch, shape):
+    """Same forward, same upstream gradient: parameter gradients of the tcgen05 backward kernel vs
+    the exact-fp32 CUDA-core backward (identical ReLU/pool decisions by construction)."""
+    B, H, W = shape
+    eng = _engine(arch)
+    rng = np.random.default_rng(33)
+    img = torch.from_numpy(rng.random((B, 3, H, W), dtype=np.float32) * 255).cuda()
+    preds = eng.forward(img, train=True)
+    d_preds = torch.from_numpy(rng.standard_normal(tuple(preds.shape)).astype(np.float32)).cuda()
+    eng.set_option('tc_backward', 0)
+    g0 = eng.backward(img, d_preds).clone()
+    eng.set_option('tc_backward', 1)
+    g1 = eng.backward(img, d_preds).clone()
+    torch.cuda.synchronize()
+    flags = eng.status_flags(B, H, W, True)
+    assert int(flags.abs().sum()) == 0, f'tensor-core kernel reported {flags[:4].tolist()}'
+    gmax = float(g0.abs().max())
+    worst = 0.0
+    for name, off, shp in eng.ctx.params():
+        n = int(np.prod(shp))
+        a, b = g1[off:off + n], g0[off:off + n]
+        scale = float(b.abs().max())
+        err = float((a - b).abs().max())
+        worst = max(worst, err / (scale + 1e-4 * gmax))
+        assert err <= 1e-4 * scale + 1e-5 * gmax, (name, err, scale)
+    print(f'{arch} {shape}: tc backward vs fp32 backward, worst normalised grad err {worst:.3e}')
