@@ -50,10 +50,14 @@ __device__ __forceinline__ void bn_coeffs_tc(const BnRef& r, int c, float& scale
   shift = r.beta[c] - m * scale;
 }
 
-template <int COUT>
+template <int COUT, int MODE>
 struct TcCfg {
+  // plain mode: two TMA landing buffers so the next tile's load overlaps the current tile's math
+  // (1 CTA / SM); pooled / up-add modes load through registers: one buffer, 2 CTAs / SM
+  static constexpr int NBUF = (MODE == 0) ? 2 : 1;
+  static constexpr int CTAS_PER_SM = (MODE == 0) ? 1 : 2;
   static constexpr uint32_t B_BLOCK = COUT * 128;          // bytes of one k-block of W1 hi (or lo)
-  static constexpr uint32_t OFF_BHI = RAW_BYTES;
+  static constexpr uint32_t OFF_BHI = NBUF * RAW_BYTES;
   static constexpr uint32_t OFF_BLO = OFF_BHI + 2 * B_BLOCK;
   static constexpr uint32_t OFF_W2 = OFF_BLO + 2 * B_BLOCK;           // [9][COUT]
   static constexpr uint32_t OFF_B1 = OFF_W2 + 9 * COUT * 4;
@@ -62,7 +66,7 @@ struct TcCfg {
   static constexpr uint32_t OFF_SH = OFF_SC + CIN * 4;
   static constexpr uint32_t OFF_SCB = OFF_SH + CIN * 4;               // up-add operand b
   static constexpr uint32_t OFF_SHB = OFF_SCB + CIN * 4;
-  static constexpr uint32_t OFF_BAR = OFF_SHB + CIN * 4;              // 3 mbarriers + tmem ptr
+  static constexpr uint32_t OFF_BAR = OFF_SHB + CIN * 4;              // 4 mbarriers + tmem ptr
   static constexpr uint32_t SMEM = OFF_BAR + 64;
   static constexpr int NQ = COUT / 4;
   static constexpr int RGN = NT / (NQ * 16);
@@ -79,13 +83,13 @@ __device__ __forceinline__ float* y_chunk(unsigned char* base, int pix, int chun
 }
 
 template <int COUT, int MODE>
-__global__ void __launch_bounds__(NT, 2)
+__global__ void __launch_bounds__(NT, (MODE == 0) ? 1 : 2)
 unit_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const UnitFwdArgs a, int* status) {
-  using C = TcCfg<COUT>;
+  using C = TcCfg<COUT, MODE>;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(
       (reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-  unsigned char* raw = smem;                                  // [2 m][2 kb][128 px][128 B]
+  unsigned char* raw0 = smem;                                 // NBUF x [2 m][2 kb][128 px][128 B]
   unsigned char* sBhi = smem + C::OFF_BHI;
   unsigned char* sBlo = smem + C::OFF_BLO;
   float* sW2 = reinterpret_cast<float*>(smem + C::OFF_W2);
@@ -95,8 +99,8 @@ unit_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const UnitFwdArgs a
   float* sSh = reinterpret_cast<float*>(smem + C::OFF_SH);
   float* sScB = reinterpret_cast<float*>(smem + C::OFF_SCB);
   float* sShB = reinterpret_cast<float*>(smem + C::OFF_SHB);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);   // [0] tma, [1] mma0, [2] mma1
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);   // [0] tma buf0, [1] mma0, [2] mma1, [3] tma buf1
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int mblk = warp >> 2;            // which M=128 block this warp converts / reads back
@@ -108,6 +112,7 @@ unit_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const UnitFwdArgs a
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
     mbar_init(&bars[2], 1);
+    mbar_init(&bars[3], 1);
     mbar_fence_init();
     tma_prefetch_desc(&tmap);
   }
@@ -156,6 +161,22 @@ unit_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const UnitFwdArgs a
   const int ntiles = tiles_x * tiles_y * a.B;
   bool alive = true;
   uint32_t it = 0;
+  // TMA: 4 boxes of (32 ch, 16 cols, 8 rows, 1 image) = 16 KB each into landing buffer `buf`
+  auto issue_tma = [&](int tile_, int buf) {
+    int t_ = tile_;
+    const int tx_ = t_ % tiles_x; t_ /= tiles_x;
+    const int ty_ = t_ % tiles_y;
+    const int b_ = t_ / tiles_y;
+    uint64_t* bar = &bars[buf == 0 ? 0 : 3];
+    unsigned char* dst = raw0 + buf * RAW_BYTES;
+    mbar_arrive_expect_tx(bar, RAW_BYTES);
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int kb = 0; kb < 2; ++kb)
+        tma_load_4d(dst + (m * 2 + kb) * 16384, &tmap, bar, kb * 32, tx_ * OT - 1, ty_ * OT - 1 + m * 8, b_);
+  };
+  if (MODE == 0 && tid == 0 && (int)blockIdx.x < ntiles) issue_tma(blockIdx.x, 0);
   for (int tile = blockIdx.x; tile < ntiles && alive; tile += gridDim.x, ++it) {
     const uint32_t ph = it & 1;
     int t = tile;
@@ -163,18 +184,14 @@ unit_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const UnitFwdArgs a
     const int ty = t % tiles_y;
     const int b = t / tiles_y;
     const int x0 = tx * OT, y0 = ty * OT;
+    const int buf = (MODE == 0) ? (int)(it & 1) : 0;
+    unsigned char* raw = raw0 + buf * RAW_BYTES;
 
     if (MODE == 0) {
-      // ---- TMA: 4 boxes of (32 ch, 16 cols, 8 rows, 1 image) = 16 KB each
-      if (tid == 0) {
-        mbar_arrive_expect_tx(&bars[0], RAW_BYTES);
-#pragma unroll
-        for (int m = 0; m < 2; ++m)
-#pragma unroll
-          for (int kb = 0; kb < 2; ++kb)
-            tma_load_4d(raw + (m * 2 + kb) * 16384, &tmap, &bars[0], kb * 32, x0 - 1, y0 - 1 + m * 8, b);
-      }
-      if (!mbar_wait(&bars[0], ph)) { alive = false; if (lane == 0) atomicExch(status, 1); }
+      // prefetch the next tile into the other buffer (its previous user finished at the barrier
+      // that ended the last iteration), then wait for this tile's data
+      if (tid == 0 && tile + (int)gridDim.x < ntiles) issue_tma(tile + gridDim.x, buf ^ 1);
+      if (!mbar_wait(&bars[buf == 0 ? 0 : 3], (it >> 1) & 1)) { alive = false; if (lane == 0) atomicExch(status, 1); }
     } else {
       // ---- pooled / up-added operand: cooperative vector loads, activation applied on the way,
       // written in the layout the TMA would have produced (row = pixel, 16 B chunks ^ (row & 7))
@@ -392,7 +409,7 @@ EncodeFn get_encode() {
 template <int COUT, int MODE>
 cudaError_t launch_tc_t(const CUtensorMap& tm, const UnitFwdArgs& a, int num_sms, int* status,
                         cudaStream_t s) {
-  using C = TcCfg<COUT>;
+  using C = TcCfg<COUT, MODE>;
   const size_t smem = C::SMEM + 1024;
   auto kern = unit_fwd_tc_kernel<COUT, MODE>;
   static bool configured = false;
@@ -402,7 +419,7 @@ cudaError_t launch_tc_t(const CUtensorMap& tm, const UnitFwdArgs& a, int num_sms
     configured = true;
   }
   const int ntiles = ((a.W + OT - 1) / OT) * ((a.H + OT - 1) / OT) * a.B;
-  int grid = 2 * num_sms;
+  int grid = C::CTAS_PER_SM * num_sms;
   if (grid > ntiles) grid = ntiles;
   kern<<<grid, NT, smem, s>>>(tm, a, status);
   return cudaGetLastError();
