@@ -2,13 +2,15 @@
 // the two pixel-major GEMMs on the 5th-gen tensor cores (sm_100a), 3xTF32 error-compensated:
 //
 //   per tile (8 x 16 halo pixels = one M=128 block, 6 x 14 interior):
-//     TMA      z_in halo tile (SWIZZLE_128B)                              -> shared
-//     LDG      du, z_out -> g = gamma*rstd*(du - mean(du) - zhat*mean(du*zhat)) -> shared (halo)
+//     TMA      z_in, du, z_out halo tiles (SWIZZLE_128B), all three PREFETCHED one tile ahead
+//              (z_in double-buffered; du / z_out land in the g / y buffers as soon as the
+//              previous tile has released them)                            -> shared
+//     g pass   g = gamma*rstd*(du - mean(du) - zhat*mean(du*zhat)) in place  (halo)
 //     convert  a = relu(bn(z_in)) row per thread -> tf32 hi/lo -> TMEM (tcgen05.st)
 //     MMA 1    y = a W1^T            (recomputed pointwise output; never stored in the forward)
 //     dw-bwd   dy = sum_k W2[k] g[q-d_k], dW2 += y g[q-d_k], db2 += g, db1 += dy   (CUDA cores)
 //     convert  dy rows -> hi/lo -> TMEM
-//     MMA 2    h = dy W1             || overlapped with ||  dW1 += dy^T a  (CUDA cores, fp32)
+//     MMA 2    h = dy W1             || overlapped with ||  dW1 += dy^T a  (warp-level 3xTF32 mma.sync)
 //     epilogue du_in = h * [u_in > 0] written once (or accumulated), sum(du_in), sum(du_in*zhat)
 //
 // Persistent CTAs (1 per SM); parameter gradients and statistics live in registers across all
@@ -35,9 +37,9 @@ constexpr uint32_t TMEM_COLS = 256;
 constexpr uint32_t COL_D1 = 0, COL_D2 = 64, COL_AHI = 128, COL_ALO = 192;
 
 struct Off {
-  static constexpr uint32_t RAW = 0;                       // z_in tile (TMA, 2 k-blocks of 16 KB)
-  static constexpr uint32_t G = RAW + TILE_BYTES;          // g halo tile   [128][64] swizzled
-  static constexpr uint32_t Y = G + TILE_BYTES;            // y -> dy tile  [128][64] swizzled
+  static constexpr uint32_t RAW = 0;                       // 2 x z_in tile (TMA, 2 k-blocks of 16 KB)
+  static constexpr uint32_t G = RAW + 2 * TILE_BYTES;      // du (TMA) -> g halo tile, TMA layout
+  static constexpr uint32_t Y = G + TILE_BYTES;            // z_out (TMA) -> y -> dy tile [128][64] swizzled
   static constexpr uint32_t B1HI = Y + TILE_BYTES;         // W1 hi  [co][ci] K-major SW128
   static constexpr uint32_t B1LO = B1HI + 16384;
   static constexpr uint32_t B2HI = B1LO + 16384;           // W1^T hi [ci][co] K-major SW128
@@ -46,7 +48,7 @@ struct Off {
   static constexpr uint32_t B1 = W2 + 9 * 64 * 4;          // bias1 [64]
   static constexpr uint32_t CA = B1 + 256;                 // scale, shift, mean, rstd of the input [4][64]
   static constexpr uint32_t CO = CA + 1024;                // gscale, m1, m2, mean, rstd of the output [5][64]
-  static constexpr uint32_t BAR = CO + 1280;               // 3 mbarriers + tmem ptr
+  static constexpr uint32_t BAR = CO + 1280;               // 6 mbarriers + tmem ptr
   static constexpr uint32_t TOTAL = BAR + 64;
 };
 
@@ -58,6 +60,18 @@ __device__ __forceinline__ float* tchunk(unsigned char* base, int pix, int chunk
 __device__ __forceinline__ const float* rchunk(const unsigned char* raw, int pix, int chunk) {
   return reinterpret_cast<const float*>(raw + (chunk >> 3) * 16384 + pix * 128 +
                                         (((chunk & 7) ^ (pix & 7)) << 4));
+}
+
+// warp-level m16n8k8 TF32 MMA (registers in / out): used for the small weight-gradient GEMM whose
+// K dimension is the pixel axis (both operands would need a transposed shared-memory copy for
+// tcgen05, which the prefetch buffers leave no room for)
+__device__ __forceinline__ void mma_m16n8k8_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0,
+                                                 uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "{%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
 struct Coef4 { float scale, shift, mean, rstd; };
@@ -74,19 +88,21 @@ __device__ __forceinline__ Coef4 bn_coef_tc(const BnRef& r, int c) {
 }
 
 __global__ void __launch_bounds__(NT, 1)
-unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const UnitBwdArgs a, int* status) {
+unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_du,
+                   const __grid_constant__ CUtensorMap tmap_zo, const UnitBwdArgs a, int* status) {
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(
       (reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-  unsigned char* raw = smem + Off::RAW;
+  unsigned char* raw0 = smem + Off::RAW;
   unsigned char* sG = smem + Off::G;
   unsigned char* sY = smem + Off::Y;
   float* sW2 = reinterpret_cast<float*>(smem + Off::W2);
   float* sB1 = reinterpret_cast<float*>(smem + Off::B1);
   float* sCa = reinterpret_cast<float*>(smem + Off::CA);
   float* sCo = reinterpret_cast<float*>(smem + Off::CO);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Off::BAR);   // tma, mma1, mma2
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3);
+  // [0],[3] z_in buffer 0/1, [1] mma1, [2] mma2, [4] du, [5] z_out
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Off::BAR);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 6);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int quarter = warp & 3;      // TMEM lane quarter
@@ -95,9 +111,10 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const UnitBwdArgs a
 
   if (warp == 0) tmem_alloc<TMEM_COLS>(tmem_ptr);
   if (tid == 0) {
-    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) mbar_init(&bars[i], 1);
     mbar_fence_init();
-    tma_prefetch_desc(&tmap);
+    tma_prefetch_desc(&tmap); tma_prefetch_desc(&tmap_du); tma_prefetch_desc(&tmap_zo);
   }
   for (int i = tid; i < 64 * 64; i += NT) {
     const int co = i / 64, ci = i % 64;
@@ -136,15 +153,17 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const UnitBwdArgs a
 #pragma unroll
   for (int k = 0; k < 9; ++k) gw2[k] = make_float4(0.f, 0.f, 0.f, 0.f);
   float4 gb2 = make_float4(0.f, 0.f, 0.f, 0.f), gb1 = gb2;
-  // dW1: 4x4 block per thread
-  const int co3 = (tid >> 4) * 4, ci3 = (tid & 15) * 4;
+  // dW1 (64 co x 64 ci) as warp-level MMA tiles: warp -> 16 co x 32 ci = four m16n8 accumulators
+  const int co0 = (warp & 3) * 16, ci0 = (warp >> 2) * 32;
+  const int fr = lane >> 2, fc = lane & 3;          // fragment row / column ids
   float gw1[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) gw1[i][j] = 0.f;
-  const float4 sc3 = *reinterpret_cast<const float4*>(sCa + ci3);
-  const float4 sh3 = *reinterpret_cast<const float4*>(sCa + 64 + ci3);
+  float scj[4], shj[4];                              // BN of the four ci this thread loads
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { scj[j] = sCa[ci0 + 8 * j + fr]; shj[j] = sCa[64 + ci0 + 8 * j + fr]; }
   // statistics of du_in: lane L of a warp owns channel half*32 + L
   double s1 = 0.0, s2 = 0.0;
 
@@ -152,34 +171,48 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const UnitBwdArgs a
   const int ntiles = tiles_x * tiles_y * a.B;
   bool alive = true;
   uint32_t it = 0;
+  auto tile_xyb = [&](int tile_, int& x0_, int& y0_, int& b_) {
+    int t_ = tile_;
+    x0_ = (t_ % tiles_x) * IC; t_ /= tiles_x;
+    y0_ = (t_ % tiles_y) * IR;
+    b_ = t_ / tiles_y;
+  };
+  auto issue = [&](const CUtensorMap* m, unsigned char* dst, uint64_t* bar, int tile_) {
+    int x0_, y0_, b_;
+    tile_xyb(tile_, x0_, y0_, b_);
+    mbar_arrive_expect_tx(bar, TILE_BYTES);
+    tma_load_4d(dst, m, bar, 0, x0_ - 1, y0_ - 1, b_);
+    tma_load_4d(dst + 16384, m, bar, 32, x0_ - 1, y0_ - 1, b_);
+  };
+  if (tid == 0 && (int)blockIdx.x < ntiles) {
+    issue(&tmap, raw0, &bars[0], blockIdx.x);
+    issue(&tmap_du, sG, &bars[4], blockIdx.x);
+    issue(&tmap_zo, sY, &bars[5], blockIdx.x);
+  }
   for (int tile = blockIdx.x; tile < ntiles && alive; tile += gridDim.x, ++it) {
     const uint32_t ph = it & 1;
-    int t = tile;
-    const int tx = t % tiles_x; t /= tiles_x;
-    const int ty = t % tiles_y;
-    const int b = t / tiles_y;
-    const int x0 = tx * IC, y0 = ty * IR;          // interior origin; halo origin = (x0-1, y0-1)
+    int x0, y0, b;
+    tile_xyb(tile, x0, y0, b);          // interior origin; halo origin = (x0-1, y0-1)
     const long long img_off = (long long)b * a.H * a.W * C64;
+    const int buf = it & 1;
+    unsigned char* raw = raw0 + buf * TILE_BYTES;
+    const int next = tile + gridDim.x;
 
-    // ---- T0: TMA for z_in, vector loads for du / z_out -> g
-    if (tid == 0) {
-      mbar_arrive_expect_tx(&bars[0], TILE_BYTES);
-      tma_load_4d(raw, &tmap, &bars[0], 0, x0 - 1, y0 - 1, b);
-      tma_load_4d(raw + 16384, &tmap, &bars[0], 32, x0 - 1, y0 - 1, b);
-    }
-    {
-      const float* dimg = a.dout + (long long)b * a.dout_batch_stride;
-      const float* zimg = a.zout + img_off;
+    // ---- T0: prefetch the next tile's z_in; turn the prefetched du / z_out tiles into g
+    if (tid == 0 && next < ntiles) issue(&tmap, raw0 + (buf ^ 1) * TILE_BYTES, &bars[buf == 0 ? 3 : 0], next);
+    if (!mbar_wait(&bars[4], ph)) { alive = false; if (lane == 0) atomicExch(status, 14); }
+    if (alive && !mbar_wait(&bars[5], ph)) { alive = false; if (lane == 0) atomicExch(status, 15); }
+    if (alive) {
 #pragma unroll 4
       for (int k = 0; k < 128 * 16 / NT; ++k) {
         const int i = tid + k * NT;
         const int pix = i >> 4, ch = i & 15;
         const int gy = y0 - 1 + pix / HC, gx = x0 - 1 + pix % HC;
+        float* gp = const_cast<float*>(rchunk(sG, pix, ch));
         float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
         if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) {
-          const long long off = ((long long)gy * a.W + gx) * C64 + ch * 4;
-          const float4 d = __ldg(reinterpret_cast<const float4*>(dimg + off));
-          const float4 z = __ldg(reinterpret_cast<const float4*>(zimg + off));
+          const float4 d = *reinterpret_cast<const float4*>(gp);
+          const float4 z = *reinterpret_cast<const float4*>(rchunk(sY, pix, ch));
           const float4 gs = *reinterpret_cast<const float4*>(sCo + ch * 4);
           const float4 m1 = *reinterpret_cast<const float4*>(sCo + 64 + ch * 4);
           const float4 m2 = *reinterpret_cast<const float4*>(sCo + 128 + ch * 4);
@@ -190,10 +223,10 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const UnitBwdArgs a
           g.z = gs.z * (d.z - m1.z - (z.z - mu.z) * rs.z * m2.z);
           g.w = gs.w * (d.w - m1.w - (z.w - mu.w) * rs.w * m2.w);
         }
-        *reinterpret_cast<float4*>(tchunk(sG, pix, ch)) = g;
+        *reinterpret_cast<float4*>(gp) = g;
       }
     }
-    if (!mbar_wait(&bars[0], ph)) { alive = false; if (lane == 0) atomicExch(status, 11); }
+    if (alive && !mbar_wait(&bars[buf == 0 ? 0 : 3], (it >> 1) & 1)) { alive = false; if (lane == 0) atomicExch(status, 11); }
 
     // ---- T1: a = relu(bn(z_in)) row per thread (32 channels per warp half) -> hi/lo -> TMEM
     const int hy = row / HC, hx = row % HC;
@@ -270,14 +303,14 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const UnitBwdArgs a
       float4 ra[3], rb[3], rc[3];
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
-        ra[d] = *reinterpret_cast<const float4*>(tchunk(sG, 0 * HC + dx + d, dq));
-        rb[d] = *reinterpret_cast<const float4*>(tchunk(sG, 1 * HC + dx + d, dq));
+        ra[d] = *reinterpret_cast<const float4*>(rchunk(sG, 0 * HC + dx + d, dq));
+        rb[d] = *reinterpret_cast<const float4*>(rchunk(sG, 1 * HC + dx + d, dq));
       }
 #pragma unroll
       for (int r = 0; r < IR; ++r) {          // interior row r <-> halo row r+1
 #pragma unroll
         for (int d = 0; d < 3; ++d)
-          rc[d] = *reinterpret_cast<const float4*>(tchunk(sG, (r + 2) * HC + dx + d, dq));
+          rc[d] = *reinterpret_cast<const float4*>(rchunk(sG, (r + 2) * HC + dx + d, dq));
         const int pix = (r + 1) * HC + dx + 1;
         const bool in = (y0 + r) < a.H && (x0 + dx) < a.W;
         const float4 y = *reinterpret_cast<const float4*>(tchunk(sY, pix, dq));
@@ -301,7 +334,9 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const UnitBwdArgs a
         for (int d = 0; d < 3; ++d) { ra[d] = rb[d]; rb[d] = rc[d]; }
       }
     }
+    fence_proxy_async_smem();      // generic writes to the g buffer precede its TMA refill
     __syncthreads();
+    if (tid == 0 && next < ntiles && alive) issue(&tmap_du, sG, &bars[4], next);
 
     // ---- T5: dy rows -> hi/lo -> TMEM (A columns are free: MMA 1 completed)
     if (alive) {
@@ -340,29 +375,43 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const UnitBwdArgs a
         }
       mma_commit(&bars[2]);
     }
-    // ---- ... while the CUDA cores do  dW1 += dy^T a  over the interior pixels
+    // ---- ... while the warps do  dW1 += dy^T a  (3xTF32 mma.sync, K = pixels; halo pixels carry
+    // dy == 0, so whole 16-pixel rows 1..6 are used: 12 k-steps of 8)
     if (alive) {
-      const int cch = co3 >> 2, ach = ci3 >> 2;
+#pragma unroll 1
       for (int r = 1; r <= IR; ++r) {
-#pragma unroll 2
-        for (int x = 1; x <= IC; ++x) {
-          const int pix = r * HC + x;
-          const float4 d4 = *reinterpret_cast<const float4*>(tchunk(sY, pix, cch));
-          const float4 z4 = *reinterpret_cast<const float4*>(rchunk(raw, pix, ach));
-          float4 a4;
-          a4.x = fmaxf(fmaf(z4.x, sc3.x, sh3.x), 0.f); a4.y = fmaxf(fmaf(z4.y, sc3.y, sh3.y), 0.f);
-          a4.z = fmaxf(fmaf(z4.z, sc3.z, sh3.z), 0.f); a4.w = fmaxf(fmaf(z4.w, sc3.w, sh3.w), 0.f);
-          const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            gw1[i][0] = fmaf(dd[i], a4.x, gw1[i][0]); gw1[i][1] = fmaf(dd[i], a4.y, gw1[i][1]);
-            gw1[i][2] = fmaf(dd[i], a4.z, gw1[i][2]); gw1[i][3] = fmaf(dd[i], a4.w, gw1[i][3]);
+        for (int xh = 0; xh < 2; ++xh) {
+          const int p0 = r * HC + xh * 8 + fc, p1 = p0 + 4;
+          uint32_t ah[4], al[4];
+          {
+            const int c0 = co0 + fr, c1 = c0 + 8;
+            const float d00 = tchunk(sY, p0, c0 >> 2)[c0 & 3], d01 = tchunk(sY, p0, c1 >> 2)[c1 & 3];
+            const float d10 = tchunk(sY, p1, c0 >> 2)[c0 & 3], d11 = tchunk(sY, p1, c1 >> 2)[c1 & 3];
+            ah[0] = tf32_hi(d00); al[0] = tf32_lo(d00);   // a0: (m = fr,     k = fc)
+            ah[1] = tf32_hi(d01); al[1] = tf32_lo(d01);   // a1: (m = fr + 8, k = fc)
+            ah[2] = tf32_hi(d10); al[2] = tf32_lo(d10);   // a2: (m = fr,     k = fc + 4)
+            ah[3] = tf32_hi(d11); al[3] = tf32_lo(d11);   // a3: (m = fr + 8, k = fc + 4)
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int ci = ci0 + 8 * j + fr;
+            const float z0 = rchunk(raw, p0, ci >> 2)[ci & 3], z1 = rchunk(raw, p1, ci >> 2)[ci & 3];
+            const float a0 = fmaxf(fmaf(z0, scj[j], shj[j]), 0.f);   // b0: (k = fc,     n = fr)
+            const float a1 = fmaxf(fmaf(z1, scj[j], shj[j]), 0.f);   // b1: (k = fc + 4, n = fr)
+            const uint32_t bh0 = tf32_hi(a0), bl0 = tf32_lo(a0), bh1 = tf32_hi(a1), bl1 = tf32_lo(a1);
+            mma_m16n8k8_tf32(gw1[j], al, bh0, bh1);
+            mma_m16n8k8_tf32(gw1[j], ah, bl0, bl1);
+            mma_m16n8k8_tf32(gw1[j], ah, bh0, bh1);
           }
         }
       }
     }
     if (alive && !mbar_wait(&bars[2], ph)) { alive = false; if (lane == 0) atomicExch(status, 13); }
     tc_fence_after();
+    fence_proxy_async_smem();      // y / dy (generic writes) precede the TMA refill of that buffer
+    __syncthreads();               // every warp is done reading dy (dW1 loop)
+    if (tid == 0 && next < ntiles && alive) issue(&tmap_zo, sY, &bars[5], next);
     // ---- T7: epilogue: du_in = h * [u_in > 0], statistics (dy of out-of-image pixels was zeroed,
     // so h is zero there; only interior in-image rows write)
     {
@@ -424,10 +473,15 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const UnitBwdArgs a
   }
 
   // ---- flush
+  // accumulator fragment: c0 (m = fr, n = 2 fc), c1 (m, n + 1), c2 (m + 8, n), c3 (m + 8, n + 1)
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) atomicAdd(a.gw1 + (co3 + i) * 64 + ci3 + j, gw1[i][j]);
+  for (int j = 0; j < 4; ++j) {
+    const int co = co0 + fr, ci = ci0 + 8 * j + 2 * fc;
+    atomicAdd(a.gw1 + co * 64 + ci, gw1[j][0]);
+    atomicAdd(a.gw1 + co * 64 + ci + 1, gw1[j][1]);
+    atomicAdd(a.gw1 + (co + 8) * 64 + ci, gw1[j][2]);
+    atomicAdd(a.gw1 + (co + 8) * 64 + ci + 1, gw1[j][3]);
+  }
   {
     float vals[44];
 #pragma unroll
@@ -481,15 +535,19 @@ int unit_bwd_tc_supported(int cin, int cout, int mode, int has_bn) {
 cudaError_t launch_unit_bwd_tc(const UnitBwdArgs& a, int num_sms, int* status, cudaStream_t s) {
   EncodeFn enc = get_encode_bwd();
   if (!enc) return cudaErrorNotSupported;
-  CUtensorMap tm;
-  cuuint64_t dims[4] = {64, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.B};
-  cuuint64_t strides[3] = {256, (cuuint64_t)a.W * 256, (cuuint64_t)a.H * a.W * 256};
-  cuuint32_t box[4] = {32, HC, HR, 1};
-  cuuint32_t es[4] = {1, 1, 1, 1};
-  CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(a.za), dims, strides, box,
-                   es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+  if (a.dout_batch_stride != (long long)a.H * a.W * C64) return cudaErrorInvalidValue;
+  CUtensorMap tm[3];
+  const float* base[3] = {a.za, a.dout, a.zout};
+  for (int i = 0; i < 3; ++i) {
+    cuuint64_t dims[4] = {64, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.B};
+    cuuint64_t strides[3] = {256, (cuuint64_t)a.W * 256, (cuuint64_t)a.H * a.W * 256};
+    cuuint32_t box[4] = {32, HC, HR, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(&tm[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base[i]), dims,
+                     strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+  }
   const size_t smem = Off::TOTAL + 1024;
   static bool configured = false;
   if (!configured) {
@@ -499,7 +557,7 @@ cudaError_t launch_unit_bwd_tc(const UnitBwdArgs& a, int num_sms, int* status, c
   }
   const int ntiles = ((a.W + IC - 1) / IC) * ((a.H + IR - 1) / IR) * a.B;
   int grid = num_sms < ntiles ? num_sms : ntiles;
-  unit_bwd_tc_kernel<<<grid, NT, smem, s>>>(tm, a, status);
+  unit_bwd_tc_kernel<<<grid, NT, smem, s>>>(tm[0], tm[1], tm[2], a, status);
   return cudaGetLastError();
 }
 

@@ -52,10 +52,12 @@ __device__ __forceinline__ void bn_coeffs_tc(const BnRef& r, int c, float& scale
 
 template <int COUT, int MODE>
 struct TcCfg {
-  // plain mode: two TMA landing buffers so the next tile's load overlaps the current tile's math
-  // (1 CTA / SM); pooled / up-add modes load through registers: one buffer, 2 CTAs / SM
-  static constexpr int NBUF = (MODE == 0) ? 2 : 1;
-  static constexpr int CTAS_PER_SM = (MODE == 0) ? 1 : 2;
+  // NBUF = 2 (plain mode only) double-buffers the TMA landing zone so the next tile's load
+  // overlaps the current tile's math, at 1 CTA / SM.  Measured on B200 (profiles/): two
+  // co-resident CTAs with a single buffer each hide more latency (0.386 ms vs 0.464 ms on the
+  // 80x80 unit) because the per-tile instruction stream, not the load, is the long pole.
+  static constexpr int NBUF = 1;
+  static constexpr int CTAS_PER_SM = (NBUF == 2) ? 1 : 2;
   static constexpr uint32_t B_BLOCK = COUT * 128;          // bytes of one k-block of W1 hi (or lo)
   static constexpr uint32_t OFF_BHI = NBUF * RAW_BYTES;
   static constexpr uint32_t OFF_BLO = OFF_BHI + 2 * B_BLOCK;
@@ -83,7 +85,7 @@ __device__ __forceinline__ float* y_chunk(unsigned char* base, int pix, int chun
 }
 
 template <int COUT, int MODE>
-__global__ void __launch_bounds__(NT, (MODE == 0) ? 1 : 2)
+__global__ void __launch_bounds__(NT, 2)
 unit_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const UnitFwdArgs a, int* status) {
   using C = TcCfg<COUT, MODE>;
   extern __shared__ unsigned char smem_dyn[];
@@ -184,14 +186,19 @@ unit_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const UnitFwdArgs a
     const int ty = t % tiles_y;
     const int b = t / tiles_y;
     const int x0 = tx * OT, y0 = ty * OT;
-    const int buf = (MODE == 0) ? (int)(it & 1) : 0;
+    const int buf = (MODE == 0 && C::NBUF == 2) ? (int)(it & 1) : 0;
     unsigned char* raw = raw0 + buf * RAW_BYTES;
 
     if (MODE == 0) {
       // prefetch the next tile into the other buffer (its previous user finished at the barrier
       // that ended the last iteration), then wait for this tile's data
-      if (tid == 0 && tile + (int)gridDim.x < ntiles) issue_tma(tile + gridDim.x, buf ^ 1);
-      if (!mbar_wait(&bars[buf == 0 ? 0 : 3], (it >> 1) & 1)) { alive = false; if (lane == 0) atomicExch(status, 1); }
+      if (C::NBUF == 2) {
+        if (tid == 0 && tile + (int)gridDim.x < ntiles) issue_tma(tile + gridDim.x, buf ^ 1);
+        if (!mbar_wait(&bars[buf == 0 ? 0 : 3], (it >> 1) & 1)) { alive = false; if (lane == 0) atomicExch(status, 1); }
+      } else {
+        if (tid == 0 && it > 0) issue_tma(tile, 0);       // tile 0 was issued before the loop
+        if (!mbar_wait(&bars[0], ph)) { alive = false; if (lane == 0) atomicExch(status, 1); }
+      }
     } else {
       // ---- pooled / up-added operand: cooperative vector loads, activation applied on the way,
       // written in the layout the TMA would have produced (row = pixel, 16 B chunks ^ (row & 7))
