@@ -474,7 +474,7 @@ int yunet_backward(yunet_ctx* ctx, const float* img, const float* params, const 
       if (u.mode == LOAD_UPADD) bytes += 4.0 * B * 2.0 * u.cin * hw / 4.0;
       const bool tc = ctx->opt_tc_backward && unit_bwd_tc_supported(u.cin, u.cout, u.mode, a.has_bn);
       Scope sc(ctx, s, (tc ? "bwd_tc:" : "bwd:") + u.name, bytes);
-      e = tc ? launch_unit_bwd_tc(a, ctx->num_sms, v.status() + 1, s)
+      e = tc ? launch_unit_bwd_tc(u.mode, a, ctx->num_sms, v.status() + 1, s)
              : launch_unit_bwd(u.cin, u.cout, u.mode, a, ctx->num_sms, s);
     }
     if (e != cudaSuccess) return fail(ctx, (int)e, "backward: unit %s: %s", u.name.c_str(), cudaGetErrorString(e));

@@ -110,7 +110,8 @@ cudaError_t launch_unit_fwd_tc(int cout, int mode, const UnitFwdArgs& a, int num
 
 // ---- unit_bwd_tc.cu: tcgen05 version of the fused unit backward (64 -> 64, plain load, BN) ----
 int unit_bwd_tc_supported(int cin, int cout, int mode, int has_bn);
-cudaError_t launch_unit_bwd_tc(const UnitBwdArgs& a, int num_sms, int* status, cudaStream_t s);
+cudaError_t launch_unit_bwd_tc(int mode, const UnitBwdArgs& a, int num_sms, int* status,
+                               cudaStream_t s);
 
 // ---- launchers (kernels_bwd.cu) ----
 cudaError_t launch_unit_bwd(int cin, int cout, int mode, const UnitBwdArgs& a, int num_sms,

@@ -47,7 +47,8 @@ struct Off {
   static constexpr uint32_t W2 = B2LO + 16384;             // [9][64]
   static constexpr uint32_t B1 = W2 + 9 * 64 * 4;          // bias1 [64]
   static constexpr uint32_t CA = B1 + 256;                 // scale, shift, mean, rstd of the input [4][64]
-  static constexpr uint32_t CO = CA + 1024;                // gscale, m1, m2, mean, rstd of the output [5][64]
+  static constexpr uint32_t CB = CA + 1024;                // same for the up-sampled operand b [4][64]
+  static constexpr uint32_t CO = CB + 1024;                // gscale, m1, m2, mean, rstd of the output [5][64]
   static constexpr uint32_t BAR = CO + 1280;               // 6 mbarriers + tmem ptr
   static constexpr uint32_t TOTAL = BAR + 64;
 };
@@ -87,6 +88,7 @@ __device__ __forceinline__ Coef4 bn_coef_tc(const BnRef& r, int c) {
   return k;
 }
 
+template <int MODE>
 __global__ void __launch_bounds__(NT, 1)
 unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_du,
                    const __grid_constant__ CUtensorMap tmap_zo, const UnitBwdArgs a, int* status) {
@@ -99,6 +101,7 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
   float* sW2 = reinterpret_cast<float*>(smem + Off::W2);
   float* sB1 = reinterpret_cast<float*>(smem + Off::B1);
   float* sCa = reinterpret_cast<float*>(smem + Off::CA);
+  float* sCb = reinterpret_cast<float*>(smem + Off::CB);
   float* sCo = reinterpret_cast<float*>(smem + Off::CO);
   // [0],[3] z_in buffer 0/1, [1] mma1, [2] mma2, [4] du, [5] z_out
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Off::BAR);
@@ -131,6 +134,10 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     sB1[tid] = __ldg(a.b1 + tid);
     const Coef4 ki = bn_coef_tc(a.bna, tid);
     sCa[tid] = ki.scale; sCa[64 + tid] = ki.shift; sCa[128 + tid] = ki.mean; sCa[192 + tid] = ki.rstd;
+    if (MODE == 2) {
+      const Coef4 kb = bn_coef_tc(a.bnb, tid);
+      sCb[tid] = kb.scale; sCb[64 + tid] = kb.shift; sCb[128 + tid] = kb.mean; sCb[192 + tid] = kb.rstd;
+    }
     const Coef4 ko = bn_coef_tc(a.bno, tid);
     sCo[tid] = a.bno.gamma[tid] * ko.rstd;
     sCo[64 + tid] = (float)(a.dsum[tid] * a.bno.inv_count);
@@ -163,7 +170,13 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     for (int j = 0; j < 4; ++j) gw1[i][j] = 0.f;
   float scj[4], shj[4];                              // BN of the four ci this thread loads
 #pragma unroll
-  for (int j = 0; j < 4; ++j) { scj[j] = sCa[ci0 + 8 * j + fr]; shj[j] = sCa[64 + ci0 + 8 * j + fr]; }
+  for (int j = 0; j < 4; ++j) {
+    scj[j] = (MODE == 0) ? sCa[ci0 + 8 * j + fr] : 1.0f;      // pooled / up-add tiles hold the
+    shj[j] = (MODE == 0) ? sCa[64 + ci0 + 8 * j + fr] : 0.0f;  // activation already (a >= 0)
+  }
+  // pooled / up-add routing: thread -> (channel quad eq, pixels tid/16 + 16k)
+  const int eq = tid & 15;
+  float4 sa1 = make_float4(0.f, 0.f, 0.f, 0.f), sa2 = sa1, sb1 = sa1, sb2 = sa1;
   // statistics of du_in: lane L of a warp owns channel half*32 + L
   double s1 = 0.0, s2 = 0.0;
 
@@ -185,7 +198,7 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     tma_load_4d(dst + 16384, m, bar, 32, x0_ - 1, y0_ - 1, b_);
   };
   if (tid == 0 && (int)blockIdx.x < ntiles) {
-    issue(&tmap, raw0, &bars[0], blockIdx.x);
+    if (MODE == 0) issue(&tmap, raw0, &bars[0], blockIdx.x);
     issue(&tmap_du, sG, &bars[4], blockIdx.x);
     issue(&tmap_zo, sY, &bars[5], blockIdx.x);
   }
@@ -194,12 +207,53 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     int x0, y0, b;
     tile_xyb(tile, x0, y0, b);          // interior origin; halo origin = (x0-1, y0-1)
     const long long img_off = (long long)b * a.H * a.W * C64;
-    const int buf = it & 1;
-    unsigned char* raw = raw0 + buf * TILE_BYTES;
+    const int buf = (MODE == 0) ? (int)(it & 1) : 0;
+    unsigned char* raw = raw0 + buf * TILE_BYTES;      // MODE 0: z_in; else: activated operand a
+    unsigned char* sH = raw0 + TILE_BYTES;             // MODE 1/2: h tile for the routing pass
     const int next = tile + gridDim.x;
 
     // ---- T0: prefetch the next tile's z_in; turn the prefetched du / z_out tiles into g
-    if (tid == 0 && next < ntiles) issue(&tmap, raw0 + (buf ^ 1) * TILE_BYTES, &bars[buf == 0 ? 3 : 0], next);
+    if (MODE == 0 && tid == 0 && next < ntiles)
+      issue(&tmap, raw0 + (buf ^ 1) * TILE_BYTES, &bars[buf == 0 ? 3 : 0], next);
+    const float* za_img = a.za + (long long)b * a.H * a.W * C64 * (MODE == 1 ? 4 : 1);
+    if (MODE != 0) {
+      // pooled / up-added operand a: vector loads (latency overlaps the waits on du / z_out)
+#pragma unroll 4
+      for (int k = 0; k < 128 * 16 / NT; ++k) {
+        const int i = tid + k * NT;
+        const int pix = i >> 4, ch = i & 15;
+        const int gy = y0 - 1 + pix / HC, gx = x0 - 1 + pix % HC;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) {
+          const float4 sc = *reinterpret_cast<const float4*>(sCa + ch * 4);
+          const float4 sh = *reinterpret_cast<const float4*>(sCa + 64 + ch * 4);
+          if (MODE == 1) {
+            const int W2 = a.W * 2;
+            const float* p = za_img + ((long long)(gy * 2) * W2 + gx * 2) * C64 + ch * 4;
+            const float4 z00 = __ldg(reinterpret_cast<const float4*>(p));
+            const float4 z01 = __ldg(reinterpret_cast<const float4*>(p + C64));
+            const float4 z10 = __ldg(reinterpret_cast<const float4*>(p + (long long)W2 * C64));
+            const float4 z11 = __ldg(reinterpret_cast<const float4*>(p + (long long)W2 * C64 + C64));
+            v.x = fmaxf(fmaxf(fmaxf(fmaf(z00.x, sc.x, sh.x), fmaf(z01.x, sc.x, sh.x)), fmaxf(fmaf(z10.x, sc.x, sh.x), fmaf(z11.x, sc.x, sh.x))), 0.f);
+            v.y = fmaxf(fmaxf(fmaxf(fmaf(z00.y, sc.y, sh.y), fmaf(z01.y, sc.y, sh.y)), fmaxf(fmaf(z10.y, sc.y, sh.y), fmaf(z11.y, sc.y, sh.y))), 0.f);
+            v.z = fmaxf(fmaxf(fmaxf(fmaf(z00.z, sc.z, sh.z), fmaf(z01.z, sc.z, sh.z)), fmaxf(fmaf(z10.z, sc.z, sh.z), fmaf(z11.z, sc.z, sh.z))), 0.f);
+            v.w = fmaxf(fmaxf(fmaxf(fmaf(z00.w, sc.w, sh.w), fmaf(z01.w, sc.w, sh.w)), fmaxf(fmaf(z10.w, sc.w, sh.w), fmaf(z11.w, sc.w, sh.w))), 0.f);
+          } else {
+            const float4 z = __ldg(reinterpret_cast<const float4*>(za_img + ((long long)gy * a.W + gx) * C64 + ch * 4));
+            const int Hb = a.H >> 1, Wb = a.W >> 1;
+            const float4 zb = __ldg(reinterpret_cast<const float4*>(
+                a.zb + (((long long)b * Hb + (gy >> 1)) * Wb + (gx >> 1)) * C64 + ch * 4));
+            const float4 scb = *reinterpret_cast<const float4*>(sCb + ch * 4);
+            const float4 shb = *reinterpret_cast<const float4*>(sCb + 64 + ch * 4);
+            v.x = fmaxf(fmaf(z.x, sc.x, sh.x), 0.f) + fmaxf(fmaf(zb.x, scb.x, shb.x), 0.f);
+            v.y = fmaxf(fmaf(z.y, sc.y, sh.y), 0.f) + fmaxf(fmaf(zb.y, scb.y, shb.y), 0.f);
+            v.z = fmaxf(fmaf(z.z, sc.z, sh.z), 0.f) + fmaxf(fmaf(zb.z, scb.z, shb.z), 0.f);
+            v.w = fmaxf(fmaf(z.w, sc.w, sh.w), 0.f) + fmaxf(fmaf(zb.w, scb.w, shb.w), 0.f);
+          }
+        }
+        *reinterpret_cast<float4*>(const_cast<float*>(rchunk(raw, pix, ch))) = v;
+      }
+    }
     if (!mbar_wait(&bars[4], ph)) { alive = false; if (lane == 0) atomicExch(status, 14); }
     if (alive && !mbar_wait(&bars[5], ph)) { alive = false; if (lane == 0) atomicExch(status, 15); }
     if (alive) {
@@ -226,7 +280,11 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         *reinterpret_cast<float4*>(gp) = g;
       }
     }
-    if (alive && !mbar_wait(&bars[buf == 0 ? 0 : 3], (it >> 1) & 1)) { alive = false; if (lane == 0) atomicExch(status, 11); }
+    if (MODE == 0) {
+      if (alive && !mbar_wait(&bars[buf == 0 ? 0 : 3], (it >> 1) & 1)) { alive = false; if (lane == 0) atomicExch(status, 11); }
+    } else {
+      __syncthreads();      // operand a staged by all threads
+    }
 
     // ---- T1: a = relu(bn(z_in)) row per thread (32 channels per warp half) -> hi/lo -> TMEM
     const int hy = row / HC, hx = row % HC;
@@ -242,8 +300,11 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
           const float4 z = *reinterpret_cast<const float4*>(rchunk(raw, row, ch));
           const float4 sc = *reinterpret_cast<const float4*>(sCa + ch * 4);
           const float4 sh = *reinterpret_cast<const float4*>(sCa + 64 + ch * 4);
-          const float v[4] = {fmaxf(fmaf(z.x, sc.x, sh.x), 0.f), fmaxf(fmaf(z.y, sc.y, sh.y), 0.f),
-                              fmaxf(fmaf(z.z, sc.z, sh.z), 0.f), fmaxf(fmaf(z.w, sc.w, sh.w), 0.f)};
+          float v[4] = {z.x, z.y, z.z, z.w};
+          if (MODE == 0) {
+            v[0] = fmaxf(fmaf(z.x, sc.x, sh.x), 0.f); v[1] = fmaxf(fmaf(z.y, sc.y, sh.y), 0.f);
+            v[2] = fmaxf(fmaf(z.z, sc.z, sh.z), 0.f); v[3] = fmaxf(fmaf(z.w, sc.w, sh.w), 0.f);
+          }
 #pragma unroll
           for (int j = 0; j < 4; ++j) { hi[c4 * 4 + j] = tf32_hi(v[j]); lo[c4 * 4 + j] = tf32_lo(v[j]); }
         }
@@ -412,6 +473,119 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     fence_proxy_async_smem();      // y / dy (generic writes) precede the TMA refill of that buffer
     __syncthreads();               // every warp is done reading dy (dW1 loop)
     if (tid == 0 && next < ntiles && alive) issue(&tmap_zo, sY, &bars[5], next);
+    if (MODE != 0) {
+      // ---- T7': h rows -> shared, then route through the max-pool winner / the up-add children
+      if (alive) {
+#pragma unroll
+        for (int g16 = 0; g16 < 2; ++g16) {
+          uint32_t hv[16];
+          tmem_ld16(lane_addr + COL_D2 + half * 32 + g16 * 16, hv);
+          tmem_wait_ld();
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4)
+            *reinterpret_cast<float4*>(tchunk(sH, row, half * 8 + g16 * 4 + c4)) =
+                make_float4(__uint_as_float(hv[c4 * 4]), __uint_as_float(hv[c4 * 4 + 1]),
+                            __uint_as_float(hv[c4 * 4 + 2]), __uint_as_float(hv[c4 * 4 + 3]));
+        }
+      }
+      __syncthreads();
+      if (alive) {
+        const float4 sc = *reinterpret_cast<const float4*>(sCa + eq * 4);
+        const float4 sh = *reinterpret_cast<const float4*>(sCa + 64 + eq * 4);
+        const float4 mu = *reinterpret_cast<const float4*>(sCa + 128 + eq * 4);
+        const float4 rs = *reinterpret_cast<const float4*>(sCa + 192 + eq * 4);
+        for (int idx = tid >> 4; idx < IR * IC; idx += NT / 16) {
+          const int r = idx / IC, x = idx % IC;
+          const int gy = y0 + r, gx = x0 + x;
+          if (gy >= a.H || gx >= a.W) continue;
+          const float4 h = *reinterpret_cast<const float4*>(tchunk(sH, (r + 1) * HC + x + 1, eq));
+          const float hh[4] = {h.x, h.y, h.z, h.w};
+          if (MODE == 2) {
+            const long long off = ((long long)gy * a.W + gx) * C64 + eq * 4;
+            const float4 z = __ldg(reinterpret_cast<const float4*>(za_img + off));
+            float4 d;
+            d.x = fmaf(z.x, sc.x, sh.x) > 0.f ? h.x : 0.f; d.y = fmaf(z.y, sc.y, sh.y) > 0.f ? h.y : 0.f;
+            d.z = fmaf(z.z, sc.z, sh.z) > 0.f ? h.z : 0.f; d.w = fmaf(z.w, sc.w, sh.w) > 0.f ? h.w : 0.f;
+            sa1.x += d.x; sa1.y += d.y; sa1.z += d.z; sa1.w += d.w;
+            sa2.x = fmaf(d.x, (z.x - mu.x) * rs.x, sa2.x); sa2.y = fmaf(d.y, (z.y - mu.y) * rs.y, sa2.y);
+            sa2.z = fmaf(d.z, (z.z - mu.z) * rs.z, sa2.z); sa2.w = fmaf(d.w, (z.w - mu.w) * rs.w, sa2.w);
+            float4* p = reinterpret_cast<float4*>(a.dua + img_off + off);
+            if (a.acc_a) { const float4 o = *p; d.x += o.x; d.y += o.y; d.z += o.z; d.w += o.w; }
+            *p = d;
+          } else {
+            // first maximum of the 2x2 window (ATen order), then the ReLU mask
+            const int W2 = a.W * 2;
+            const long long o00 = ((long long)(gy * 2) * W2 + gx * 2) * C64 + eq * 4;
+            const long long offs[4] = {o00, o00 + C64, o00 + (long long)W2 * C64, o00 + (long long)W2 * C64 + C64};
+            float zz[4][4], vv[4][4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 z = __ldg(reinterpret_cast<const float4*>(za_img + offs[j]));
+              zz[j][0] = z.x; zz[j][1] = z.y; zz[j][2] = z.z; zz[j][3] = z.w;
+              vv[j][0] = fmaxf(fmaf(z.x, sc.x, sh.x), 0.f); vv[j][1] = fmaxf(fmaf(z.y, sc.y, sh.y), 0.f);
+              vv[j][2] = fmaxf(fmaf(z.z, sc.z, sh.z), 0.f); vv[j][3] = fmaxf(fmaf(z.w, sc.w, sh.w), 0.f);
+            }
+            const float muv[4] = {mu.x, mu.y, mu.z, mu.w}, rsv[4] = {rs.x, rs.y, rs.z, rs.w};
+            float dd[4][4], s1v[4], s2v[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              float best = vv[0][c]; int bj = 0;
+#pragma unroll
+              for (int j = 1; j < 4; ++j) if (vv[j][c] > best) { best = vv[j][c]; bj = j; }
+              const float hv = best > 0.f ? hh[c] : 0.f;
+              float zb = zz[0][c];
+#pragma unroll
+              for (int j = 1; j < 4; ++j) if (j == bj) zb = zz[j][c];
+              s1v[c] = hv;
+              s2v[c] = hv * ((zb - muv[c]) * rsv[c]);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) dd[j][c] = (j == bj) ? hv : 0.f;
+            }
+            sa1.x += s1v[0]; sa1.y += s1v[1]; sa1.z += s1v[2]; sa1.w += s1v[3];
+            sa2.x += s2v[0]; sa2.y += s2v[1]; sa2.z += s2v[2]; sa2.w += s2v[3];
+            float* dbase = a.dua + (long long)b * a.H * a.W * C64 * 4;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float4 o = make_float4(dd[j][0], dd[j][1], dd[j][2], dd[j][3]);
+              float4* p = reinterpret_cast<float4*>(dbase + offs[j]);
+              if (a.acc_a) { const float4 q = *p; o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w; }
+              *p = o;
+            }
+          }
+        }
+        if (MODE == 2) {
+          // up-sampled operand: a low-res pixel gathers its 2x2 children (tile origin is even)
+          const float4 scb = *reinterpret_cast<const float4*>(sCb + eq * 4);
+          const float4 shb = *reinterpret_cast<const float4*>(sCb + 64 + eq * 4);
+          const float4 mub = *reinterpret_cast<const float4*>(sCb + 128 + eq * 4);
+          const float4 rsb = *reinterpret_cast<const float4*>(sCb + 192 + eq * 4);
+          const int Hb = a.H >> 1, Wb = a.W >> 1;
+          for (int idx = tid >> 4; idx < (IR / 2) * (IC / 2); idx += NT / 16) {
+            const int ly = idx / (IC / 2), lx = idx % (IC / 2);
+            const int gy = (y0 >> 1) + ly, gx = (x0 >> 1) + lx;
+            if (gy >= Hb || gx >= Wb) continue;
+            const int p00 = (2 * ly + 1) * HC + 2 * lx + 1;
+            const float4 h0 = *reinterpret_cast<const float4*>(tchunk(sH, p00, eq));
+            const float4 h1 = *reinterpret_cast<const float4*>(tchunk(sH, p00 + 1, eq));
+            const float4 h2 = *reinterpret_cast<const float4*>(tchunk(sH, p00 + HC, eq));
+            const float4 h3 = *reinterpret_cast<const float4*>(tchunk(sH, p00 + HC + 1, eq));
+            const float4 hs = make_float4(h0.x + h1.x + h2.x + h3.x, h0.y + h1.y + h2.y + h3.y,
+                                          h0.z + h1.z + h2.z + h3.z, h0.w + h1.w + h2.w + h3.w);
+            const long long off = (((long long)b * Hb + gy) * Wb + gx) * C64 + eq * 4;
+            const float4 z = __ldg(reinterpret_cast<const float4*>(a.zb + off));
+            float4 d;
+            d.x = fmaf(z.x, scb.x, shb.x) > 0.f ? hs.x : 0.f; d.y = fmaf(z.y, scb.y, shb.y) > 0.f ? hs.y : 0.f;
+            d.z = fmaf(z.z, scb.z, shb.z) > 0.f ? hs.z : 0.f; d.w = fmaf(z.w, scb.w, shb.w) > 0.f ? hs.w : 0.f;
+            sb1.x += d.x; sb1.y += d.y; sb1.z += d.z; sb1.w += d.w;
+            sb2.x = fmaf(d.x, (z.x - mub.x) * rsb.x, sb2.x); sb2.y = fmaf(d.y, (z.y - mub.y) * rsb.y, sb2.y);
+            sb2.z = fmaf(d.z, (z.z - mub.z) * rsb.z, sb2.z); sb2.w = fmaf(d.w, (z.w - mub.w) * rsb.w, sb2.w);
+            float4* p = reinterpret_cast<float4*>(a.dub + off);
+            if (a.acc_b) { const float4 o = *p; d.x += o.x; d.y += o.y; d.z += o.z; d.w += o.w; }
+            *p = d;
+          }
+        }
+      }
+    } else
     // ---- T7: epilogue: du_in = h * [u_in > 0], statistics (dy of out-of-image pixels was zeroed,
     // so h is zero there; only interior in-image rows write)
     {
@@ -502,8 +676,26 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
       }
     }
   }
-  atomicAdd(a.dsum_a + half * 32 + lane, s1);
-  atomicAdd(a.dsumzh_a + half * 32 + lane, s2);
+  if (MODE == 0) {
+    atomicAdd(a.dsum_a + half * 32 + lane, s1);
+    atomicAdd(a.dsumzh_a + half * 32 + lane, s2);
+  } else {
+    float vals[16] = {sa1.x, sa1.y, sa1.z, sa1.w, sa2.x, sa2.y, sa2.z, sa2.w,
+                      sb1.x, sb1.y, sb1.z, sb1.w, sb2.x, sb2.y, sb2.z, sb2.w};
+#pragma unroll
+    for (int v = 0; v < 16; ++v) vals[v] += __shfl_xor_sync(0xffffffffu, vals[v], 16);
+    if (lane < 16) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        atomicAdd(a.dsum_a + eq * 4 + c, (double)vals[c]);
+        atomicAdd(a.dsumzh_a + eq * 4 + c, (double)vals[4 + c]);
+        if (MODE == 2) {
+          atomicAdd(a.dsum_b + eq * 4 + c, (double)vals[8 + c]);
+          atomicAdd(a.dsumzh_b + eq * 4 + c, (double)vals[12 + c]);
+        }
+      }
+    }
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc<TMEM_COLS>(tbase);
@@ -529,16 +721,17 @@ EncodeFn get_encode_bwd() {
 }  // namespace
 
 int unit_bwd_tc_supported(int cin, int cout, int mode, int has_bn) {
-  return cin == 64 && cout == 64 && mode == 0 && has_bn && get_encode_bwd() != nullptr;
+  return cin == 64 && cout == 64 && mode >= 0 && mode <= 2 && has_bn && get_encode_bwd() != nullptr;
 }
 
-cudaError_t launch_unit_bwd_tc(const UnitBwdArgs& a, int num_sms, int* status, cudaStream_t s) {
+cudaError_t launch_unit_bwd_tc(int mode, const UnitBwdArgs& a, int num_sms, int* status, cudaStream_t s) {
   EncodeFn enc = get_encode_bwd();
   if (!enc) return cudaErrorNotSupported;
   if (a.dout_batch_stride != (long long)a.H * a.W * C64) return cudaErrorInvalidValue;
   CUtensorMap tm[3];
+  memset(tm, 0, sizeof tm);
   const float* base[3] = {a.za, a.dout, a.zout};
-  for (int i = 0; i < 3; ++i) {
+  for (int i = (mode == 0 ? 0 : 1); i < 3; ++i) {
     cuuint64_t dims[4] = {64, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.B};
     cuuint64_t strides[3] = {256, (cuuint64_t)a.W * 256, (cuuint64_t)a.H * a.W * 256};
     cuuint32_t box[4] = {32, HC, HR, 1};
@@ -549,16 +742,18 @@ cudaError_t launch_unit_bwd_tc(const UnitBwdArgs& a, int num_sms, int* status, c
     if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
   }
   const size_t smem = Off::TOTAL + 1024;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(unit_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
   const int ntiles = ((a.W + IC - 1) / IC) * ((a.H + IR - 1) / IR) * a.B;
-  int grid = num_sms < ntiles ? num_sms : ntiles;
-  unit_bwd_tc_kernel<<<grid, NT, smem, s>>>(tm[0], tm[1], tm[2], a, status);
-  return cudaGetLastError();
+  const int grid = num_sms < ntiles ? num_sms : ntiles;
+  auto go = [&](auto kern) -> cudaError_t {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, NT, smem, s>>>(tm[0], tm[1], tm[2], a, status);
+    return cudaGetLastError();
+  };
+  if (mode == 0) return go(unit_bwd_tc_kernel<0>);
+  if (mode == 1) return go(unit_bwd_tc_kernel<1>);
+  if (mode == 2) return go(unit_bwd_tc_kernel<2>);
+  return cudaErrorInvalidValue;
 }
 
 }  // namespace yunet
