@@ -24,10 +24,6 @@ namespace yunet {
 
 namespace {
 
-constexpr int TH = 8, TW = 16;
-constexpr int HH = TH + 2, HW = TW + 2;
-constexpr int HP = HH * HW;   // 180
-constexpr int TP = TH * TW;   // 128 interior pixels
 constexpr int NT = 256;
 
 struct Coef {  // per-channel BN constants of an input tensor
@@ -77,6 +73,13 @@ __device__ __forceinline__ float comp(const float4& v, int i) {
 
 template <int CIN, int COUT>
 struct BwdCfg {
+  // interior tile 8 x 16; the 16 -> 16 units (160^2 / 80^2 layers) take 16 x 16 so that the
+  // per-tile barriers and load latency are amortised over twice the pixels at equal occupancy
+  static constexpr bool BIG = (CIN <= 16 && COUT <= 16);
+  static constexpr int TH = BIG ? 16 : 8, TW = 16;
+  static constexpr int HH = TH + 2, HW = TW + 2;
+  static constexpr int HP = HH * HW;   // 180 (324) halo pixels
+  static constexpr int TP = TH * TW;   // 128 (256) interior pixels
   static constexpr int AS = CIN + 4;
   static constexpr int YS = COUT + 4;
   // GEMM1: N = COUT
@@ -111,10 +114,10 @@ __global__ void __launch_bounds__(NT, (CIN * COUT <= 1024) ? 2 : 1) unit_bwd_ker
   using C = BwdCfg<CIN, COUT>;
   extern __shared__ float4 smem_raw[];
   float* smem = reinterpret_cast<float*>(smem_raw);
-  float* sG = smem;                        // [HP][COUT]
-  float* sA = sG + HP * COUT;              // [TP][AS]     (later h)
-  float* sY = sA + TP * C::AS;             // [TP][YS]     (y, then dy)
-  float* sW1 = sY + TP * C::YS;            // [COUT][CIN]
+  float* sG = smem;                        // [C::HP][COUT]
+  float* sA = sG + C::HP * COUT;              // [C::TP][AS]     (later h)
+  float* sY = sA + C::TP * C::AS;             // [C::TP][YS]     (y, then dy)
+  float* sW1 = sY + C::TP * C::YS;            // [COUT][CIN]
   float* sW1t = sW1 + CIN * COUT;          // [CIN][COUT]
   float* sW2 = sW1t + CIN * COUT;          // [9][COUT]
   float* sB1 = sW2 + 9 * COUT;             // [COUT]
@@ -159,8 +162,8 @@ __global__ void __launch_bounds__(NT, (CIN * COUT <= 1024) ? 2 : 1) unit_bwd_ker
   // ---- persistent accumulators
   // depthwise-stage mapping
   const int dq = tid % C::NQ;
-  const int dx = (tid / C::NQ) % TW;
-  const int dr0 = (tid / (C::NQ * TW)) * C::RPT;
+  const int dx = (tid / C::NQ) % C::TW;
+  const int dr0 = (tid / (C::NQ * C::TW)) * C::RPT;
   float4 gw2[9];
 #pragma unroll
   for (int k = 0; k < 9; ++k) gw2[k] = f4(0.f);
@@ -179,8 +182,8 @@ __global__ void __launch_bounds__(NT, (CIN * COUT <= 1024) ? 2 : 1) unit_bwd_ker
   const int eq = tid % C::QI;
   float4 sa1 = f4(0.f), sa2 = f4(0.f), sb1 = f4(0.f), sb2 = f4(0.f);
 
-  const int tiles_x = (a.W + TW - 1) / TW;
-  const int tiles_y = (a.H + TH - 1) / TH;
+  const int tiles_x = (a.W + C::TW - 1) / C::TW;
+  const int tiles_y = (a.H + C::TH - 1) / C::TH;
   const int ntiles = tiles_x * tiles_y * a.B;
   const long long in_img_stride = (MODE == 1) ? (long long)a.H * a.W * 4 * CIN : (long long)a.H * a.W * CIN;
 
@@ -189,7 +192,7 @@ __global__ void __launch_bounds__(NT, (CIN * COUT <= 1024) ? 2 : 1) unit_bwd_ker
     const int tx = t % tiles_x; t /= tiles_x;
     const int ty = t % tiles_y;
     const int b = t / tiles_y;
-    const int x0 = tx * TW, y0 = ty * TH;
+    const int x0 = tx * C::TW, y0 = ty * C::TH;
     const float* za_img = a.za + (long long)b * in_img_stride;
 
     // ---- S0a: g on the halo tile
@@ -198,11 +201,11 @@ __global__ void __launch_bounds__(NT, (CIN * COUT <= 1024) ? 2 : 1) unit_bwd_ker
       const float* dimg = a.dout + (long long)b * a.dout_batch_stride;
       const float* zimg = HAS_BN ? a.zout + (long long)b * a.H * a.W * COUT : nullptr;
 #pragma unroll 4
-      for (int it = 0; it < (HP * Q + NT - 1) / NT; ++it) {
+      for (int it = 0; it < (C::HP * Q + NT - 1) / NT; ++it) {
         const int i = tid + it * NT;
-        if (i >= HP * Q) break;
+        if (i >= C::HP * Q) break;
         const int pix = i / Q, q = i % Q;
-        const int gy = y0 + pix / HW - 1, gx = x0 + pix % HW - 1;
+        const int gy = y0 + pix / C::HW - 1, gx = x0 + pix % C::HW - 1;
         float4 g = f4(0.f);
         if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) {
           const long long off = ((long long)gy * a.W + gx) * COUT + q * 4;
@@ -225,10 +228,10 @@ __global__ void __launch_bounds__(NT, (CIN * COUT <= 1024) ? 2 : 1) unit_bwd_ker
     {
       constexpr int Q = CIN / 4;
 #pragma unroll 4
-      for (int it = 0; it < TP * Q / NT; ++it) {
+      for (int it = 0; it < C::TP * Q / NT; ++it) {
         const int i = tid + it * NT;
         const int pix = i / Q, q = i % Q;
-        const int gy = y0 + pix / TW, gx = x0 + pix % TW;
+        const int gy = y0 + pix / C::TW, gx = x0 + pix % C::TW;
         float4 v = f4(0.f);
         if (gy < a.H && gx < a.W) {
           const float4 sc = lds4(sCa + q * 4), sh = lds4(sCa + CIN + q * 4);
@@ -290,7 +293,7 @@ __global__ void __launch_bounds__(NT, (CIN * COUT <= 1024) ? 2 : 1) unit_bwd_ker
 #pragma unroll
       for (int i = 0; i < C::PPT1; ++i) {
         const int pix = pg + i * C::NPG1;
-        const int gy = y0 + pix / TW, gx = x0 + pix % TW;
+        const int gy = y0 + pix / C::TW, gx = x0 + pix % C::TW;
         const bool in = gy < a.H && gx < a.W;
 #pragma unroll
         for (int j4 = 0; j4 < C::CPT1 / 4; ++j4) {
@@ -314,17 +317,17 @@ __global__ void __launch_bounds__(NT, (CIN * COUT <= 1024) ? 2 : 1) unit_bwd_ker
       float4 ra[3], rb[3], rc[3];
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
-        ra[d] = lds4(sG + ((dr0 + 0) * HW + dx + d) * COUT + dq * 4);
-        rb[d] = lds4(sG + ((dr0 + 1) * HW + dx + d) * COUT + dq * 4);
+        ra[d] = lds4(sG + ((dr0 + 0) * C::HW + dx + d) * COUT + dq * 4);
+        rb[d] = lds4(sG + ((dr0 + 1) * C::HW + dx + d) * COUT + dq * 4);
       }
       const int gx = x0 + dx;
 #pragma unroll
       for (int i = 0; i < C::RPT; ++i) {
 #pragma unroll
         for (int d = 0; d < 3; ++d)
-          rc[d] = lds4(sG + ((dr0 + i + 2) * HW + dx + d) * COUT + dq * 4);
+          rc[d] = lds4(sG + ((dr0 + i + 2) * C::HW + dx + d) * COUT + dq * 4);
         const int r = dr0 + i;
-        const int pix = r * TW + dx;
+        const int pix = r * C::TW + dx;
         const bool in = (y0 + r) < a.H && gx < a.W;
         const float4 y = lds4(sY + pix * C::YS + dq * 4);
         float4 dy = f4(0.f);
@@ -379,7 +382,7 @@ __global__ void __launch_bounds__(NT, (CIN * COUT <= 1024) ? 2 : 1) unit_bwd_ker
       }
       // GEMM3: pixels g3, g3+G3, ...
 #pragma unroll 4
-      for (int p = g3; p < TP; p += C::G3) {
+      for (int p = g3; p < C::TP; p += C::G3) {
         const float4 d4 = lds4(sY + p * C::YS + co3);
         const float4 a4 = lds4(sA + p * C::AS + ci3);
 #pragma unroll
@@ -411,7 +414,7 @@ __global__ void __launch_bounds__(NT, (CIN * COUT <= 1024) ? 2 : 1) unit_bwd_ker
 #pragma unroll
       for (int it = 0; it < C::EPT; ++it) {
         const int pix = (tid + it * NT) / C::QI;
-        const int gy = y0 + pix / TW, gx = x0 + pix % TW;
+        const int gy = y0 + pix / C::TW, gx = x0 + pix % C::TW;
         if (gy >= a.H || gx >= a.W) continue;
         const float4 h = lds4(sA + pix * C::AS + eq * 4);
         if (MODE == 0 || MODE == 2) {
@@ -474,16 +477,16 @@ __global__ void __launch_bounds__(NT, (CIN * COUT <= 1024) ? 2 : 1) unit_bwd_ker
         const float4 scb = lds4(sCb + eq * 4), shb = lds4(sCb + CIN + eq * 4);
         const float4 mub = lds4(sCb + 2 * CIN + eq * 4), rsb = lds4(sCb + 3 * CIN + eq * 4);
         const int Hb = a.H >> 1, Wb = a.W >> 1;
-        for (int idx = tid; idx < (TP / 4) * C::QI; idx += NT) {
-          const int lp = idx / C::QI;                 // 0..31 : (TH/2) x (TW/2)
-          const int ly = lp / (TW / 2), lx = lp % (TW / 2);
+        for (int idx = tid; idx < (C::TP / 4) * C::QI; idx += NT) {
+          const int lp = idx / C::QI;                 // 0..31 : (C::TH/2) x (C::TW/2)
+          const int ly = lp / (C::TW / 2), lx = lp % (C::TW / 2);
           const int gy = (y0 >> 1) + ly, gx = (x0 >> 1) + lx;
           if (gy >= Hb || gx >= Wb) continue;
-          const int p00 = (ly * 2) * TW + lx * 2;
+          const int p00 = (ly * 2) * C::TW + lx * 2;
           float4 hs = lds4(sA + p00 * C::AS + eq * 4);
           hs = add4(hs, lds4(sA + (p00 + 1) * C::AS + eq * 4));
-          hs = add4(hs, lds4(sA + (p00 + TW) * C::AS + eq * 4));
-          hs = add4(hs, lds4(sA + (p00 + TW + 1) * C::AS + eq * 4));
+          hs = add4(hs, lds4(sA + (p00 + C::TW) * C::AS + eq * 4));
+          hs = add4(hs, lds4(sA + (p00 + C::TW + 1) * C::AS + eq * 4));
           const long long off = (((long long)b * Hb + gy) * Wb + gx) * CIN + eq * 4;
           const float4 z = ldg4(a.zb + off);
           const float4 u = bnu4(z, scb, shb);
@@ -674,7 +677,7 @@ cudaError_t launch_unit_bwd_t(const UnitBwdArgs& a, int num_sms, cudaStream_t s)
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  const int ntiles = ((a.W + TW - 1) / TW) * ((a.H + TH - 1) / TH) * a.B;
+  const int ntiles = ((a.W + C::TW - 1) / C::TW) * ((a.H + C::TH - 1) / C::TH) * a.B;
   const int per_sm = (CIN * COUT <= 1024) ? 2 : 1;
   int grid = per_sm * num_sms < ntiles ? per_sm * num_sms : ntiles;
   kern<<<grid, NT, smem, s>>>(a);

@@ -20,10 +20,6 @@ namespace yunet {
 
 namespace {
 
-constexpr int TH = 8, TW = 16;              // output tile
-constexpr int HH = TH + 2, HW = TW + 2;     // halo tile
-constexpr int HP = HH * HW;                 // 180 halo pixels
-constexpr int HPP = 192;                    // padded to the GEMM's pixel blocking
 constexpr int NT = 256;
 
 __device__ __forceinline__ void bn_coeffs(const BnRef& r, int c, float& scale, float& shift) {
@@ -69,6 +65,14 @@ __device__ __forceinline__ float4 ldg4(const float* p) {
 
 template <int CIN, int COUT>
 struct FwdCfg {
+  // output tile: 8 x 16 pixels; the 16-channel units (the 160^2 / 80^2 layers: few FLOPs, many
+  // pixels) take 16 x 32 so the per-tile barriers and the exposed load latency are amortised
+  // over 4x the pixels
+  static constexpr bool BIG = (CIN <= 16 && COUT <= 16);
+  static constexpr int TH = BIG ? 16 : 8, TW = BIG ? 32 : 16;
+  static constexpr int HH = TH + 2, HW = TW + 2;     // halo tile
+  static constexpr int HP = HH * HW;                 // 180 (612) halo pixels
+  static constexpr int HPP = BIG ? 640 : 192;        // padded to the GEMM's pixel blocking
   static constexpr int CPT = (COUT == 16) ? 4 : 8;   // output channels per thread in the GEMM
   static constexpr int NCG = COUT / CPT;             // channel groups
   static constexpr int NPG = NT / NCG;               // pixel groups
@@ -88,8 +92,8 @@ __global__ void __launch_bounds__(NT, 2) unit_fwd_kernel(const UnitFwdArgs a) {
   using C = FwdCfg<CIN, COUT>;
   extern __shared__ float4 smem_raw[];
   float* smem = reinterpret_cast<float*>(smem_raw);
-  float* sA = smem;                       // [HPP][AS]
-  float* sY = smem;                       // [HP][COUT]   (aliases sA after the GEMM)
+  float* sA = smem;                       // [C::HPP][AS]
+  float* sY = smem;                       // [C::HP][COUT]   (aliases sA after the GEMM)
   float* sW1t = smem + C::R0;             // [CIN][COUT]
   float* sW2 = sW1t + CIN * COUT;         // [9][COUT]
   float* sB1 = sW2 + 9 * COUT;            // [COUT]
@@ -100,8 +104,8 @@ __global__ void __launch_bounds__(NT, 2) unit_fwd_kernel(const UnitFwdArgs a) {
   float* sShB = sScB + CIN;
 
   const int tid = threadIdx.x;
-  const int tiles_x = (a.W + TW - 1) / TW;
-  const int tiles_y = (a.H + TH - 1) / TH;
+  const int tiles_x = (a.W + C::TW - 1) / C::TW;
+  const int tiles_y = (a.H + C::TH - 1) / C::TH;
   const int ntiles = tiles_x * tiles_y * a.B;
 
   // ---- stage 0 (once per persistent CTA): weights + BN coefficients into shared memory
@@ -129,8 +133,8 @@ __global__ void __launch_bounds__(NT, 2) unit_fwd_kernel(const UnitFwdArgs a) {
 
   // depthwise-stage mapping, weights in registers, BatchNorm statistics accumulated over all tiles
   const int dq = tid % C::NQ;
-  const int dx = (tid / C::NQ) % TW;
-  const int dr0 = (tid / (C::NQ * TW)) * C::RPT;
+  const int dx = (tid / C::NQ) % C::TW;
+  const int dr0 = (tid / (C::NQ * C::TW)) * C::RPT;
   double st1[4] = {0.0, 0.0, 0.0, 0.0}, st2[4] = {0.0, 0.0, 0.0, 0.0};
 
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -138,21 +142,21 @@ __global__ void __launch_bounds__(NT, 2) unit_fwd_kernel(const UnitFwdArgs a) {
   const int tx = t % tiles_x; t /= tiles_x;
   const int ty = t % tiles_y;
   const int b = t / tiles_y;
-  const int x0 = tx * TW, y0 = ty * TH;
+  const int x0 = tx * C::TW, y0 = ty * C::TH;
 
   // ---- stage 1: halo tile of activated inputs -> sA
   {
     constexpr int Q = CIN / 4;
-    static_assert((HPP * Q) % NT == 0, "prologue trip count");
+    static_assert((C::HPP * Q) % NT == 0, "prologue trip count");
     // fixed trip count + partial unroll: the global loads of several iterations are in flight
     // together instead of one dependent load per iteration
 #pragma unroll 4
-    for (int it = 0; it < HPP * Q / NT; ++it) {
+    for (int it = 0; it < C::HPP * Q / NT; ++it) {
       const int i = tid + it * NT;
       const int pix = i / Q, q = i % Q;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (pix < HP) {
-        const int hy = pix / HW, hx = pix % HW;
+      if (pix < C::HP) {
+        const int hy = pix / C::HW, hx = pix % C::HW;
         const int gy = y0 + hy - 1, gx = x0 + hx - 1;
         if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) {
           const float4 sc = *reinterpret_cast<const float4*>(sScA + q * 4);
@@ -221,8 +225,8 @@ __global__ void __launch_bounds__(NT, 2) unit_fwd_kernel(const UnitFwdArgs a) {
 #pragma unroll
   for (int i = 0; i < C::PPT; ++i) {
     const int pix = pg + i * C::NPG;
-    if (pix < HP) {
-      const int hy = pix / HW, hx = pix % HW;
+    if (pix < C::HP) {
+      const int hy = pix / C::HW, hx = pix % C::HW;
       const int gy = y0 + hy - 1, gx = x0 + hx - 1;
       const bool in = gy >= 0 && gy < a.H && gx >= 0 && gx < a.W;
 #pragma unroll
@@ -248,8 +252,8 @@ __global__ void __launch_bounds__(NT, 2) unit_fwd_kernel(const UnitFwdArgs a) {
     float4 ra[3], rb[3], rc[3];
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-      ra[d] = *reinterpret_cast<const float4*>(sY + ((dr0 + 0) * HW + dx + d) * COUT + dq * 4);
-      rb[d] = *reinterpret_cast<const float4*>(sY + ((dr0 + 1) * HW + dx + d) * COUT + dq * 4);
+      ra[d] = *reinterpret_cast<const float4*>(sY + ((dr0 + 0) * C::HW + dx + d) * COUT + dq * 4);
+      rb[d] = *reinterpret_cast<const float4*>(sY + ((dr0 + 1) * C::HW + dx + d) * COUT + dq * 4);
     }
     float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
     const int gx = x0 + dx;
@@ -257,7 +261,7 @@ __global__ void __launch_bounds__(NT, 2) unit_fwd_kernel(const UnitFwdArgs a) {
     for (int i = 0; i < C::RPT; ++i) {
 #pragma unroll
       for (int d = 0; d < 3; ++d)
-        rc[d] = *reinterpret_cast<const float4*>(sY + ((dr0 + i + 2) * HW + dx + d) * COUT + dq * 4);
+        rc[d] = *reinterpret_cast<const float4*>(sY + ((dr0 + i + 2) * C::HW + dx + d) * COUT + dq * 4);
       float4 o = bias;
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
@@ -480,7 +484,7 @@ cudaError_t launch_unit_fwd_t(const UnitFwdArgs& a, int num_sms, cudaStream_t s)
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  const int tiles = ((a.W + TW - 1) / TW) * ((a.H + TH - 1) / TH) * a.B;
+  const int tiles = ((a.W + C::TW - 1) / C::TW) * ((a.H + C::TH - 1) / C::TH) * a.B;
   int grid = 2 * num_sms;            // persistent: __launch_bounds__(NT, 2)
   if (grid > tiles) grid = tiles;
   kern<<<grid, NT, smem, s>>>(a);
