@@ -46,6 +46,9 @@ def parse():
     ap.add_argument('--cpu-sample', type=int, default=32, help='images per CPU-baseline step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--kernel-table', default='', help='write the per-kernel profile here (json)')
+    ap.add_argument('--workload', default='train', choices=['train', 'infer'],
+                    help="'train' (default, the headline metric) or 'infer': BASELINE.json "
+                         "configs[3], eval forward + decode + NMS at 640x640, bs=512")
     return ap.parse_args()
 
 
@@ -359,8 +362,47 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_infer(args):
+    """BASELINE.json configs[3]: yunet_n 640x640 inference-only throughput, bs=512, incl. NMS."""
+    from libfacedetection.train_b200 import YuNetEngine
+    torch.cuda.set_device(0)
+    B = 512 if args.batch == 256 else args.batch
+    S = 640 if args.size == 320 else args.size
+    eng = YuNetEngine(args.arch)
+    gold = os.path.join(ROOT, 'tests', 'golden', f'weights_{args.arch}.npz')
+    d = np.load(gold)
+    eng.load_state_dict({k: torch.from_numpy(d[k]) for k in d.files})
+    g = torch.Generator(device='cuda').manual_seed(0)
+    img = torch.rand(B, 3, S, S, device='cuda', generator=g) * 255
+    K, Wm = args.steps, max(args.warmup, 3)
+    for _ in range(Wm):
+        eng.detect(img)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        dets, counts, _ = eng.detect(img)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / K
+    peak, src = measured_peaks()
+    alg = 112.15e6 * B * (S / 640.0) ** 2      # SURVEY 8(d): forward algorithmic bytes / image @640
+    print(json.dumps({
+        'metric': 'infer_images_per_sec_640', 'value': B / (ms / 1e3), 'unit': UNIT, 'n_gpus': 1,
+        'steps': K, 'warmup': Wm, 'ms_per_step': ms, 'higher_is_better': True, 'dtype': 'f32',
+        'data': 'synthetic', 'config': {'workload': f'{args.arch} {S}x{S} eval forward + decode + '
+                                        f'NMS, bs={B} (BASELINE.json configs[3])'},
+        'detections_per_image': float(counts.float().mean()),
+        'roofline': {'bound': 'hbm', 'achieved': alg / 1e9 / (ms / 1e3), 'peak': peak, 'unit': 'GB/s',
+                     'frac': alg / 1e9 / (ms / 1e3) / peak, 'peak_source': src,
+                     'note': 'whole forward+NMS step against the forward algorithmic bytes'}}),
+        flush=True)
+
+
 def main():
     args = parse()
+    if args.workload == 'infer' and args.impl != 'reference':
+        return run_infer(args)
     if args.impl == 'reference':
         run_reference(args)
     else:
