@@ -175,7 +175,9 @@ def run_ours(args):
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+        import datetime
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local),
+                                timeout=datetime.timedelta(seconds=180))
     dev = torch.device('cuda', local)
     B, S, K, Wm = args.batch, args.size, args.steps, max(args.warmup, 3)
 
@@ -272,11 +274,13 @@ def run_ours(args):
 
     # ---------------- per-kernel profile (separate pass, per-launch CUDA events on the stream)
     kern = {}
+    reps = 3
     if rank == 0:
         lib.yunet_profile_begin(eng.h)
-        reps = 3
-        for i in range(reps):
-            eng.train_step(*devb[i % 2], lr=LR)
+    for i in range(reps):          # every rank steps (the step contains collectives)
+        eng.train_step(*devb[i % 2], lr=LR)
+    torch.cuda.synchronize()
+    if rank == 0:
         n = lib.yunet_profile_end(eng.h)
         name = C.create_string_buffer(160)
         ms = C.c_float()
