@@ -309,7 +309,7 @@ def run_ours(args):
     step_ms = sum(r['ms'] for r in table)
     streaming = [r for r in table if r['gbs'] is not None]
     dom = streaming[0] if streaming else None
-    fwd = [r for r in streaming if r['kernel'].startswith('fwd:')]
+    fwd = [r for r in streaming if r['kernel'].startswith('fwd')]
     fwd_bytes = sum(r['algorithmic_bytes'] for r in fwd)
     fwd_ms = sum(r['ms'] for r in fwd)
     all_bytes = sum(r['algorithmic_bytes'] for r in streaming)

@@ -361,20 +361,28 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
       float4 w2r[9];
 #pragma unroll
       for (int k = 0; k < 9; ++k) w2r[k] = *reinterpret_cast<const float4*>(sW2 + k * 64 + dq * 4);
+      // swizzle terms depend only on the pixel column (tile width 16, 16 % 8 == 0): column base
+      // pointers once, immediate row offsets in the unrolled loop
+      const unsigned char* gcol[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const int px = dx + d;
+        gcol[d] = sG + (dq >> 3) * 16384 + px * 128 + (((dq & 7) ^ (px & 7)) << 4);
+      }
+      unsigned char* ycol = sY + (HC + dx + 1) * 256 + ((dq ^ ((dx + 1) & 7)) << 4);
       float4 ra[3], rb[3], rc[3];
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
-        ra[d] = *reinterpret_cast<const float4*>(rchunk(sG, 0 * HC + dx + d, dq));
-        rb[d] = *reinterpret_cast<const float4*>(rchunk(sG, 1 * HC + dx + d, dq));
+        ra[d] = *reinterpret_cast<const float4*>(gcol[d]);
+        rb[d] = *reinterpret_cast<const float4*>(gcol[d] + HC * 128);
       }
 #pragma unroll
       for (int r = 0; r < IR; ++r) {          // interior row r <-> halo row r+1
 #pragma unroll
         for (int d = 0; d < 3; ++d)
-          rc[d] = *reinterpret_cast<const float4*>(rchunk(sG, (r + 2) * HC + dx + d, dq));
-        const int pix = (r + 1) * HC + dx + 1;
+          rc[d] = *reinterpret_cast<const float4*>(gcol[d] + (r + 2) * HC * 128);
         const bool in = (y0 + r) < a.H && (x0 + dx) < a.W;
-        const float4 y = *reinterpret_cast<const float4*>(tchunk(sY, pix, dq));
+        const float4 y = *reinterpret_cast<const float4*>(ycol + r * HC * 256);
         float4 dy = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
@@ -390,7 +398,7 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         gb2.x += rb[1].x; gb2.y += rb[1].y; gb2.z += rb[1].z; gb2.w += rb[1].w;
         if (!in) dy = make_float4(0.f, 0.f, 0.f, 0.f);
         gb1.x += dy.x; gb1.y += dy.y; gb1.z += dy.z; gb1.w += dy.w;
-        *reinterpret_cast<float4*>(tchunk(sY, pix, dq)) = dy;
+        *reinterpret_cast<float4*>(ycol + r * HC * 256) = dy;
 #pragma unroll
         for (int d = 0; d < 3; ++d) { ra[d] = rb[d]; rb[d] = rc[d]; }
       }
@@ -439,16 +447,31 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     // ---- ... while the warps do  dW1 += dy^T a  (3xTF32 mma.sync, K = pixels; halo pixels carry
     // dy == 0, so whole 16-pixel rows 1..6 are used: 12 k-steps of 8)
     if (alive) {
+      // pixel p0 = r*16 + xh*8 + fc has (p0 & 7) == fc and p1 = p0 + 4 has (p1 & 7) == fc ^ 4:
+      // per-thread byte offsets inside a pixel row are loop-invariant
+      const int c0 = co0 + fr, c1 = c0 + 8;
+      const int oa00 = (((c0 >> 2) ^ fc) << 4) + (c0 & 3) * 4, oa01 = (((c1 >> 2) ^ fc) << 4) + (c1 & 3) * 4;
+      const int oa10 = (((c0 >> 2) ^ fc ^ 4) << 4) + (c0 & 3) * 4, oa11 = (((c1 >> 2) ^ fc ^ 4) << 4) + (c1 & 3) * 4;
+      int ob0[4], ob1[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int ci = ci0 + 8 * j + fr, chn = ci >> 2;
+        ob0[j] = (chn >> 3) * 16384 + (((chn & 7) ^ fc) << 4) + (ci & 3) * 4;
+        ob1[j] = (chn >> 3) * 16384 + (((chn & 7) ^ fc ^ 4) << 4) + (ci & 3) * 4;
+      }
 #pragma unroll 1
       for (int r = 1; r <= IR; ++r) {
 #pragma unroll
         for (int xh = 0; xh < 2; ++xh) {
           const int p0 = r * HC + xh * 8 + fc, p1 = p0 + 4;
+          const unsigned char* yr0 = sY + p0 * 256;
+          const unsigned char* yr1 = sY + p1 * 256;
+          const unsigned char* zr0 = raw + p0 * 128;
+          const unsigned char* zr1 = raw + p1 * 128;
           uint32_t ah[4], al[4];
           {
-            const int c0 = co0 + fr, c1 = c0 + 8;
-            const float d00 = tchunk(sY, p0, c0 >> 2)[c0 & 3], d01 = tchunk(sY, p0, c1 >> 2)[c1 & 3];
-            const float d10 = tchunk(sY, p1, c0 >> 2)[c0 & 3], d11 = tchunk(sY, p1, c1 >> 2)[c1 & 3];
+            const float d00 = *reinterpret_cast<const float*>(yr0 + oa00), d01 = *reinterpret_cast<const float*>(yr0 + oa01);
+            const float d10 = *reinterpret_cast<const float*>(yr1 + oa10), d11 = *reinterpret_cast<const float*>(yr1 + oa11);
             ah[0] = tf32_hi(d00); al[0] = tf32_lo(d00);   // a0: (m = fr,     k = fc)
             ah[1] = tf32_hi(d01); al[1] = tf32_lo(d01);   // a1: (m = fr + 8, k = fc)
             ah[2] = tf32_hi(d10); al[2] = tf32_lo(d10);   // a2: (m = fr,     k = fc + 4)
@@ -456,8 +479,8 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const int ci = ci0 + 8 * j + fr;
-            const float z0 = rchunk(raw, p0, ci >> 2)[ci & 3], z1 = rchunk(raw, p1, ci >> 2)[ci & 3];
+            const float z0 = *reinterpret_cast<const float*>(zr0 + ob0[j]);
+            const float z1 = *reinterpret_cast<const float*>(zr1 + ob1[j]);
             const float a0 = fmaxf(fmaf(z0, scj[j], shj[j]), 0.f);   // b0: (k = fc,     n = fr)
             const float a1 = fmaxf(fmaf(z1, scj[j], shj[j]), 0.f);   // b1: (k = fc + 4, n = fr)
             const uint32_t bh0 = tf32_hi(a0), bl0 = tf32_lo(a0), bh1 = tf32_hi(a1), bl1 = tf32_lo(a1);

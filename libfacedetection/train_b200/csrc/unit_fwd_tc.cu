@@ -308,6 +308,8 @@ unit_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const UnitFwdArgs a
       const int gy = y0 - 1 + pix / HT, gx = x0 - 1 + pix % HT;
       const bool in = gy >= 0 && gy < a.H && gx >= 0 && gx < a.W;
       const uint32_t dcol = lane_addr + (mblk == 0 ? COL_D0 : COL_D1);
+      unsigned char* ybase = raw + pix * (COUT * 4);
+      const int yx = (pix & ((COUT == 64) ? 7 : 3)) << 4;
 #pragma unroll
       for (int g = 0; g < COUT / 16; ++g) {
         uint32_t v[16];
@@ -321,47 +323,61 @@ unit_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const UnitFwdArgs a
           o.y = in ? __uint_as_float(v[c4 * 4 + 1]) + bb.y : 0.f;
           o.z = in ? __uint_as_float(v[c4 * 4 + 2]) + bb.z : 0.f;
           o.w = in ? __uint_as_float(v[c4 * 4 + 3]) + bb.w : 0.f;
-          *reinterpret_cast<float4*>(y_chunk<COUT>(raw, pix, g * 4 + c4)) = o;
+          *reinterpret_cast<float4*>(ybase + (((g * 4 + c4) << 4) ^ yx)) = o;
         }
       }
     }
     tc_fence_before();
     __syncthreads();
 
-    // ---- depthwise 3x3 on the 16x16 y tile -> 14x14 outputs, store z, statistics
+    // ---- depthwise 3x3 on the 16x16 y tile -> 14x14 outputs, store z, statistics.
+    // The swizzle term of a y-tile address depends only on the pixel COLUMN (the tile is 16 wide
+    // and 16 % 8 == 0), so three column base pointers are formed once and the fully unrolled row
+    // loop uses immediate offsets.
     if (alive && dx < OT && dr0 < OT) {
+      constexpr int ROWB = COUT * 4;
+      constexpr int MASK = (COUT == 64) ? 7 : 3;
+      constexpr int RS = HT * ROWB;            // bytes between tile rows
+      const unsigned char* col[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const int px = dx + d;
+        col[d] = raw + (dr0 * HT + px) * ROWB + ((dq ^ (px & MASK)) << 4);
+      }
       float4 ra[3], rb[3], rc[3];
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
-        ra[d] = *reinterpret_cast<const float4*>(y_chunk<COUT>(raw, (dr0 + 0) * HT + dx + d, dq));
-        rb[d] = *reinterpret_cast<const float4*>(y_chunk<COUT>(raw, (dr0 + 1) * HT + dx + d, dq));
+        ra[d] = *reinterpret_cast<const float4*>(col[d]);
+        rb[d] = *reinterpret_cast<const float4*>(col[d] + RS);
       }
       float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
       const int gx = x0 + dx;
-      for (int rr = dr0; rr < dr1; ++rr) {
+      float* dst0 = a.zout + (long long)b * a.out_batch_stride + ((long long)(y0 + dr0) * a.W + gx) * COUT + dq * 4;
+      const long long dst_rs = (long long)a.W * COUT;
 #pragma unroll
-        for (int d = 0; d < 3; ++d)
-          rc[d] = *reinterpret_cast<const float4*>(y_chunk<COUT>(raw, (rr + 2) * HT + dx + d, dq));
-        float4 o = bias2;
+      for (int i = 0; i < C::RPT; ++i) {
+        if (dr0 + i < dr1) {
 #pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          o.x = fmaf(w2r[d].x, ra[d].x, o.x); o.y = fmaf(w2r[d].y, ra[d].y, o.y);
-          o.z = fmaf(w2r[d].z, ra[d].z, o.z); o.w = fmaf(w2r[d].w, ra[d].w, o.w);
-          o.x = fmaf(w2r[3 + d].x, rb[d].x, o.x); o.y = fmaf(w2r[3 + d].y, rb[d].y, o.y);
-          o.z = fmaf(w2r[3 + d].z, rb[d].z, o.z); o.w = fmaf(w2r[3 + d].w, rb[d].w, o.w);
-          o.x = fmaf(w2r[6 + d].x, rc[d].x, o.x); o.y = fmaf(w2r[6 + d].y, rc[d].y, o.y);
-          o.z = fmaf(w2r[6 + d].z, rc[d].z, o.z); o.w = fmaf(w2r[6 + d].w, rc[d].w, o.w);
+          for (int d = 0; d < 3; ++d) rc[d] = *reinterpret_cast<const float4*>(col[d] + (i + 2) * RS);
+          float4 o = bias2;
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            o.x = fmaf(w2r[d].x, ra[d].x, o.x); o.y = fmaf(w2r[d].y, ra[d].y, o.y);
+            o.z = fmaf(w2r[d].z, ra[d].z, o.z); o.w = fmaf(w2r[d].w, ra[d].w, o.w);
+            o.x = fmaf(w2r[3 + d].x, rb[d].x, o.x); o.y = fmaf(w2r[3 + d].y, rb[d].y, o.y);
+            o.z = fmaf(w2r[3 + d].z, rb[d].z, o.z); o.w = fmaf(w2r[3 + d].w, rb[d].w, o.w);
+            o.x = fmaf(w2r[6 + d].x, rc[d].x, o.x); o.y = fmaf(w2r[6 + d].y, rc[d].y, o.y);
+            o.z = fmaf(w2r[6 + d].z, rc[d].z, o.z); o.w = fmaf(w2r[6 + d].w, rc[d].w, o.w);
+          }
+          if (y0 + dr0 + i < a.H && gx < a.W) {
+            *reinterpret_cast<float4*>(dst0 + i * dst_rs) = o;
+            s1.x += o.x; s1.y += o.y; s1.z += o.z; s1.w += o.w;
+            s2.x = fmaf(o.x, o.x, s2.x); s2.y = fmaf(o.y, o.y, s2.y);
+            s2.z = fmaf(o.z, o.z, s2.z); s2.w = fmaf(o.w, o.w, s2.w);
+          }
+#pragma unroll
+          for (int d = 0; d < 3; ++d) { ra[d] = rb[d]; rb[d] = rc[d]; }
         }
-        const int gy = y0 + rr;
-        if (gy < a.H && gx < a.W) {
-          float* dst = a.zout + (long long)b * a.out_batch_stride + ((long long)gy * a.W + gx) * COUT + dq * 4;
-          *reinterpret_cast<float4*>(dst) = o;
-          s1.x += o.x; s1.y += o.y; s1.z += o.z; s1.w += o.w;
-          s2.x = fmaf(o.x, o.x, s2.x); s2.y = fmaf(o.y, o.y, s2.y);
-          s2.z = fmaf(o.z, o.z, s2.z); s2.w = fmaf(o.w, o.w, s2.w);
-        }
-#pragma unroll
-        for (int d = 0; d < 3; ++d) { ra[d] = rb[d]; rb[d] = rc[d]; }
       }
       st1[0] += s1.x; st1[1] += s1.y; st1[2] += s1.z; st1[3] += s1.w;
       st2[0] += s2.x; st2[1] += s2.y; st2[2] += s2.z; st2[3] += s2.w;
