@@ -76,6 +76,7 @@ struct Views {
   float* z(int t) const { return reinterpret_cast<float*>(ws + L.z_off[t]); }
   float* du(int t) const { return reinterpret_cast<float*>(ws + L.du_off[t]); }
   int* status() const { return reinterpret_cast<int*>(ws + L.status_off); }
+  float* partial() const { return reinterpret_cast<float*>(ws + L.partial_off); }
   double* stat(int which) const {
     return reinterpret_cast<double*>(ws + L.stats_off) + (size_t)which * p.num_bn_ch;
   }
@@ -467,6 +468,9 @@ int yunet_backward(yunet_ctx* ctx, const float* img, const float* params, const 
     }
     a.gw1 = grad_bucket + u.w1; a.gb1 = grad_bucket + u.b1;
     a.gw2 = grad_bucket + u.w2; a.gb2 = grad_bucket + u.b2;
+    a.partial = v.partial();
+    if (u.b1 != u.w1 + (long long)u.cout * u.cin || u.w2 != u.b1 + u.cout || u.b2 != u.w2 + 9LL * u.cout)
+      return fail(ctx, -4, "backward: unit %s: parameter group is not contiguous", u.name.c_str());
     {
       const double hw = (double)a.H * a.W;
       double bytes = 4.0 * B * (2.0 * u.cin * hw * (u.mode == LOAD_POOL ? 4.0 : 1.0) +
@@ -486,6 +490,8 @@ int yunet_backward(yunet_ctx* ctx, const float* img, const float* params, const 
     const BnDesc& bn = p.bns[p.tensors[p.stem_out].bn];
     a.dsum = v.stat(2) + bn.ch_off; a.dsumzh = v.stat(3) + bn.ch_off;
     a.gw = grad_bucket + p.stem_w; a.gb = grad_bucket + p.stem_b;
+    a.partial = v.partial();
+    if (p.stem_b != p.stem_w + 432) return fail(ctx, -4, "backward: stem parameters are not contiguous");
     a.B = B; a.Hin = H; a.Win = W;
     Scope sc(ctx, s, "bwd:stem", 4.0 * B * (3.0 * H * W + 2.0 * 16.0 * (H / 2) * (W / 2)));
     e = launch_stem_bwd(a, ctx->num_sms, s);

@@ -54,8 +54,12 @@ struct UnitBwdArgs {
   int acc_a, acc_b;             // accumulate (1) or overwrite (0)
   double* dsum_a; double* dsumzh_a;   // statistics of dua for the producer's BN backward
   double* dsum_b; double* dsumzh_b;
-  // parameter gradients (atomically accumulated; bucket zeroed before backward)
+  // parameter gradients: every CTA reduces its contributions in shared memory and writes ONE
+  // partial vector [gw1 | gb1 | gw2 | gb2] to partial[blockIdx.x * kPartialStride]; a follow-up
+  // reduce kernel sums the partials into the gradient bucket (no contended global atomics,
+  // bit-reproducible sums)
   float* gw1; float* gb1; float* gw2; float* gb2;
+  float* partial;
   int B, H, W;
   int has_bn;
 };
@@ -69,6 +73,9 @@ struct StemArgs {
   int B, Hin, Win;
 };
 
+constexpr int kPartialStride = 5120;   // floats per CTA partial (>= 64*64 + 11*64)
+constexpr int kMaxPartialCtas = 512;
+
 struct StemBwdArgs {
   const float* img;
   const float* zout;     // pre-BN stem output
@@ -76,6 +83,7 @@ struct StemBwdArgs {
   BnRef bno;
   const double* dsum; const double* dsumzh;
   float* gw; float* gb;
+  float* partial;
   int B, Hin, Win;
 };
 
@@ -117,6 +125,8 @@ cudaError_t launch_unit_bwd_tc(int mode, const UnitBwdArgs& a, int num_sms, int*
 cudaError_t launch_unit_bwd(int cin, int cout, int mode, const UnitBwdArgs& a, int num_sms,
                             cudaStream_t s);
 cudaError_t launch_stem_bwd(const StemBwdArgs& a, int num_sms, cudaStream_t s);
+// out[i] = sum_c partial[c * kPartialStride + i], i < n   (deterministic parameter-gradient flush)
+cudaError_t launch_reduce_partials(const float* partial, int ncta, int n, float* out, cudaStream_t s);
 // d(gamma) = sum(du*zhat), d(beta) = sum(du) for every BN, from the statistics area
 cudaError_t launch_bn_param_grads(const BnFinalizeArgs& a, const double* dsum,
                                   const double* dsumzh, float* grad_bucket, cudaStream_t s);

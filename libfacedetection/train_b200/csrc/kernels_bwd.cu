@@ -505,15 +505,18 @@ __global__ void __launch_bounds__(NT, (CIN * COUT <= 1024) ? 2 : 1) unit_bwd_ker
     __syncthreads();   // sA (h) and sG are rewritten by the next tile
   }
 
-  // ---- flush: parameter gradients and input-gradient statistics
-  // dW1: one 4x4 block per thread (pixel-split groups add up through the atomics)
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) atomicAdd(a.gw1 + (co3 + i) * CIN + ci3 + j, gw1[i][j]);
-  // dW2 / db2 / db1: lanes sharing a channel quad inside the warp reduce first
+  // ---- flush: parameter gradients -> shared-memory reduction -> one partial vector per CTA
   {
-    constexpr int NQ = C::NQ;   // 4, 8 or 16 lanes hold distinct quads; lanes l, l+NQ, ... share
+    constexpr int NW1 = COUT * CIN, NP = NW1 + 11 * COUT;
+    float* sRed = smem;                       // the tile buffers are free now
+    __syncthreads();
+    for (int i = tid; i < NP; i += NT) sRed[i] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) atomicAdd(sRed + (co3 + i) * CIN + ci3 + j, gw1[i][j]);
+    constexpr int NQ = C::NQ;   // lanes l, l+NQ, ... of a warp share a channel quad: reduce first
     float vals[44];
 #pragma unroll
     for (int k = 0; k < 9; ++k) { vals[k * 4] = gw2[k].x; vals[k * 4 + 1] = gw2[k].y; vals[k * 4 + 2] = gw2[k].z; vals[k * 4 + 3] = gw2[k].w; }
@@ -528,13 +531,16 @@ __global__ void __launch_bounds__(NT, (CIN * COUT <= 1024) ? 2 : 1) unit_bwd_ker
 #pragma unroll
       for (int k = 0; k < 9; ++k)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) atomicAdd(a.gw2 + (dq * 4 + c) * 9 + k, vals[k * 4 + c]);
+        for (int c = 0; c < 4; ++c) atomicAdd(sRed + NW1 + COUT + (dq * 4 + c) * 9 + k, vals[k * 4 + c]);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        atomicAdd(a.gb2 + dq * 4 + c, vals[36 + c]);
-        atomicAdd(a.gb1 + dq * 4 + c, vals[40 + c]);
+        atomicAdd(sRed + NW1 + 10 * COUT + dq * 4 + c, vals[36 + c]);   // gb2
+        atomicAdd(sRed + NW1 + dq * 4 + c, vals[40 + c]);               // gb1
       }
     }
+    __syncthreads();
+    float* dst = a.partial + (long long)blockIdx.x * kPartialStride;
+    for (int i = tid; i < NP; i += NT) dst[i] = sRed[i];
   }
   {
     constexpr int QI = C::QI;
@@ -648,14 +654,38 @@ __global__ void __launch_bounds__(256, 3) stem_bwd_kernel(const StemBwdArgs a) {
     }
     __syncthreads();
   }
+  // flush: shared-memory reduction, one partial vector [gw (432) | gb (16)] per CTA
+  float* sRed = &sGs[0][0];
+  __syncthreads();
+  for (int i = tid; i < 448; i += 256) sRed[i] = 0.f;
+  __syncthreads();
   if (tid < 252) {
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx)
-        atomicAdd(a.gw + (coq * 4 + i) * 27 + c * 9 + ky * 3 + kx, acc[i][kx]);
+        atomicAdd(sRed + (coq * 4 + i) * 27 + c * 9 + ky * 3 + kx, acc[i][kx]);
   }
-  atomicAdd(a.gb + (tid & 15), bsum);
+  atomicAdd(sRed + 432 + (tid & 15), bsum);
+  __syncthreads();
+  float* dst = a.partial + (long long)blockIdx.x * kPartialStride;
+  for (int i = tid; i < 448; i += 256) dst[i] = sRed[i];
+}
+
+__global__ void reduce_partials_kernel(const float* __restrict__ partial, int ncta, int n,
+                                       float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int c = 0;
+  for (; c + 3 < ncta; c += 4) {
+    s0 += partial[(long long)(c + 0) * kPartialStride + i];
+    s1 += partial[(long long)(c + 1) * kPartialStride + i];
+    s2 += partial[(long long)(c + 2) * kPartialStride + i];
+    s3 += partial[(long long)(c + 3) * kPartialStride + i];
+  }
+  for (; c < ncta; ++c) s0 += partial[(long long)c * kPartialStride + i];
+  out[i] = (s0 + s1) + (s2 + s3);
 }
 
 __global__ void bn_param_grads_kernel(const BnFinalizeArgs a, const double* dsum,
@@ -680,8 +710,12 @@ cudaError_t launch_unit_bwd_t(const UnitBwdArgs& a, int num_sms, cudaStream_t s)
   const int ntiles = ((a.W + C::TW - 1) / C::TW) * ((a.H + C::TH - 1) / C::TH) * a.B;
   const int per_sm = (CIN * COUT <= 1024) ? 2 : 1;
   int grid = per_sm * num_sms < ntiles ? per_sm * num_sms : ntiles;
+  if (grid > kMaxPartialCtas) grid = kMaxPartialCtas;
   kern<<<grid, NT, smem, s>>>(a);
-  return cudaGetLastError();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  // gw1, gb1, gw2, gb2 are adjacent in the bucket in this order (plan.cpp)
+  return launch_reduce_partials(a.partial, grid, COUT * CIN + 11 * COUT, a.gw1, s);
 }
 
 template <int CIN, int COUT>
@@ -716,7 +750,15 @@ cudaError_t launch_stem_bwd(const StemBwdArgs& a, int num_sms, cudaStream_t s) {
   const int Ho = a.Hin / 2, Wo = a.Win / 2;
   const int ntiles = ((Wo + ST_TW - 1) / ST_TW) * ((Ho + ST_TH - 1) / ST_TH) * a.B;
   int grid = 3 * num_sms < ntiles ? 3 * num_sms : ntiles;
+  if (grid > kMaxPartialCtas) grid = kMaxPartialCtas;
   stem_bwd_kernel<<<grid, 256, 0, s>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  return launch_reduce_partials(a.partial, grid, 448, a.gw, s);   // [weight (432) | bias (16)]
+}
+
+cudaError_t launch_reduce_partials(const float* partial, int ncta, int n, float* out, cudaStream_t s) {
+  reduce_partials_kernel<<<(n + 127) / 128, 128, 0, s>>>(partial, ncta, n, out);
   return cudaGetLastError();
 }
 

@@ -237,6 +237,8 @@ WsLayout make_layout(const Plan& p, int B, int H, int W, bool train) {
   cur = align(cur + L.stats_bytes);
   L.status_off = cur;
   cur = align(cur + 256);
+  L.partial_off = cur;
+  if (train) cur = align(cur + sizeof(float) * 512 * 5120);   // kMaxPartialCtas x kPartialStride
   L.total = cur;
   int off = 0;
   for (int l = 0; l < 3; ++l) {

@@ -80,6 +80,7 @@ struct WsLayout {
   size_t stats_off = 0;         // double [4][num_bn_ch]: sum, sumsq, dsum, dsum_zh
   size_t stats_bytes = 0;
   size_t status_off = 0;        // int[64]: device-side error flags (bounded waits of the TC kernels)
+  size_t partial_off = 0;       // per-CTA parameter-gradient partials (train only)
   size_t total = 0;
   int P = 0;
   int level_off[3] = {0, 0, 0};  // prior offset of each level

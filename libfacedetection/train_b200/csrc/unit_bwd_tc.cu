@@ -669,17 +669,22 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     alive = __syncthreads_and(alive ? 1 : 0) != 0;
   }
 
-  // ---- flush
-  // accumulator fragment: c0 (m = fr, n = 2 fc), c1 (m, n + 1), c2 (m + 8, n), c3 (m + 8, n + 1)
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int co = co0 + fr, ci = ci0 + 8 * j + 2 * fc;
-    atomicAdd(a.gw1 + co * 64 + ci, gw1[j][0]);
-    atomicAdd(a.gw1 + co * 64 + ci + 1, gw1[j][1]);
-    atomicAdd(a.gw1 + (co + 8) * 64 + ci, gw1[j][2]);
-    atomicAdd(a.gw1 + (co + 8) * 64 + ci + 1, gw1[j][3]);
-  }
+  // ---- flush: parameter gradients -> shared-memory reduction -> one partial vector per CTA
   {
+    constexpr int NW1 = 64 * 64, NP = NW1 + 11 * 64;
+    float* sRed = reinterpret_cast<float*>(raw0);      // tile buffers are free (no TMA in flight)
+    __syncthreads();
+    for (int i = tid; i < NP; i += NT) sRed[i] = 0.f;
+    __syncthreads();
+    // accumulator fragment: c0 (m = fr, n = 2 fc), c1 (m, n + 1), c2 (m + 8, n), c3 (m + 8, n + 1)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int co = co0 + fr, ci = ci0 + 8 * j + 2 * fc;
+      sRed[co * 64 + ci] = gw1[j][0];
+      sRed[co * 64 + ci + 1] = gw1[j][1];
+      sRed[(co + 8) * 64 + ci] = gw1[j][2];
+      sRed[(co + 8) * 64 + ci + 1] = gw1[j][3];
+    }
     float vals[44];
 #pragma unroll
     for (int k = 0; k < 9; ++k) { vals[k * 4] = gw2[k].x; vals[k * 4 + 1] = gw2[k].y; vals[k * 4 + 2] = gw2[k].z; vals[k * 4 + 3] = gw2[k].w; }
@@ -691,13 +696,16 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
 #pragma unroll
       for (int k = 0; k < 9; ++k)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) atomicAdd(a.gw2 + (dq * 4 + c) * 9 + k, vals[k * 4 + c]);
+        for (int c = 0; c < 4; ++c) atomicAdd(sRed + NW1 + 64 + (dq * 4 + c) * 9 + k, vals[k * 4 + c]);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        atomicAdd(a.gb2 + dq * 4 + c, vals[36 + c]);
-        atomicAdd(a.gb1 + dq * 4 + c, vals[40 + c]);
+        atomicAdd(sRed + NW1 + 640 + dq * 4 + c, vals[36 + c]);   // gb2
+        atomicAdd(sRed + NW1 + dq * 4 + c, vals[40 + c]);         // gb1
       }
     }
+    __syncthreads();
+    float* dst = a.partial + (long long)blockIdx.x * kPartialStride;
+    for (int i = tid; i < NP; i += NT) dst[i] = sRed[i];
   }
   if (MODE == 0) {
     atomicAdd(a.dsum_a + half * 32 + lane, s1);
@@ -771,7 +779,9 @@ cudaError_t launch_unit_bwd_tc(int mode, const UnitBwdArgs& a, int num_sms, int*
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, NT, smem, s>>>(tm[0], tm[1], tm[2], a, status);
-    return cudaGetLastError();
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    return launch_reduce_partials(a.partial, grid, 64 * 64 + 11 * 64, a.gw1, s);
   };
   if (mode == 0) return go(unit_bwd_tc_kernel<0>);
   if (mode == 1) return go(unit_bwd_tc_kernel<1>);
