@@ -1,12 +1,16 @@
 #!/bin/bash
+# ncu evidence for profiles/ (one GPU; numbers printed under ncu are never bench values)
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_tc.py tests/test_gpu_parity.py -m gpu -q -rA -p no:cacheprovider -k "tc or golden" > gpurun_out/pytest_tc.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_tc.log
-grep -E "^(FAILED|ERROR)|passed|failed|tensor-core kernel reported" gpurun_out/pytest_tc.log | tail -12
-timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --kernel-table gpurun_out/kernels.json > gpurun_out/bench.log 2>&1
-tail -1 gpurun_out/bench.log | cut -c1-200
-# launch list of two plain steps (cold-cache, serialised: shares only)
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python tools/profile_step.py 2 > gpurun_out/ncu_launch.log 2>&1
-# full capture: tensor-core forward + backward unit kernels of the second step (largest units come first in bwd)
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:unit_bwd_tc_kernel -s 9 -c 3 -o gpurun_out/prof_bwd_tc python tools/profile_step.py 2 > gpurun_out/ncu_bwd.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:unit_fwd_tc_kernel -s 14 -c 4 -o gpurun_out/prof_fwd_tc python tools/profile_step.py 2 > gpurun_out/ncu_fwd.log 2>&1
-ls -la gpurun_out/
+P="python tools/profile_step.py 2"
+N="ncu --set full --clock-control none --import-source on"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv $P > gpurun_out/ncu_launch.log 2>&1
+# second step only (first step = warm-up): the two 80x80 64->64 units are launches 13,14 of the
+# 14 unit_bwd_tc launches of a step and launches 1,2 of the 17 unit_fwd_tc launches
+timeout 600 $N -k regex:unit_bwd_tc_kernel -s 26 -c 2 -o gpurun_out/prof_bwd_tc $P > gpurun_out/ncu_bwd_tc.log 2>&1
+timeout 600 $N -k regex:unit_fwd_tc_kernel -s 17 -c 2 -o gpurun_out/prof_fwd_tc $P > gpurun_out/ncu_fwd_tc.log 2>&1
+# fp32 units of the 160x160 / 80x80 layers: backward launches 4..6 of 6, forward launches 1..3 of 3
+timeout 600 $N -k regex:unit_bwd_kernel -s 9 -c 3 -o gpurun_out/prof_bwd_fp32 $P > gpurun_out/ncu_bwd_fp32.log 2>&1
+timeout 600 $N -k regex:unit_fwd_kernel -s 3 -c 3 -o gpurun_out/prof_fwd_fp32 $P > gpurun_out/ncu_fwd_fp32.log 2>&1
+timeout 600 $N -k regex:stem_ -s 2 -c 2 -o gpurun_out/prof_stem $P > gpurun_out/ncu_stem.log 2>&1
+timeout 600 $N -k regex:simota_assign -s 1 -c 1 -o gpurun_out/prof_simota $P > gpurun_out/ncu_simota.log 2>&1
+ls -la gpurun_out/*.ncu-rep
