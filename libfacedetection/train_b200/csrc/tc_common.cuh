@@ -131,13 +131,30 @@ __device__ __forceinline__ uint64_t make_desc_sw128_kmajor(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                                // layout type: SWIZZLE_128B
   return d;
 }
-// Instruction descriptor for kind::tf32, fp32 accumulate, both operands K-major, M x N tile.
-__host__ __device__ constexpr uint32_t make_idesc_tf32(uint32_t M, uint32_t N) {
+// MN-major operand (the M / N index is the contiguous one), 128-byte swizzle: 32 tf32 of M/N per
+// 128-byte row, 8 K-rows per 1024-byte swizzle atom; blocks of 32 M/N elements are `lbo_bytes`
+// apart, groups of 8 K-rows `sbo_bytes` apart.  A pixel-major [kblock][pixel][32 ch] tile as the
+// TMA writes it IS this layout with K = pixel: lbo = bytes per channel block, sbo = 1024.
+__device__ __forceinline__ uint64_t make_desc_sw128_mnmajor(uint32_t smem_addr, uint32_t lbo_bytes,
+                                                            uint32_t sbo_bytes = 1024,
+                                                            uint32_t layout_type = 2) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout_type << 61;     // 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B (32-bit MN-major)
+  return d;
+}
+// Instruction descriptor for kind::tf32, fp32 accumulate, M x N tile; a_mn / b_mn = 1 selects an
+// MN-major shared-memory operand (0 = K-major).
+__host__ __device__ constexpr uint32_t make_idesc_tf32(uint32_t M, uint32_t N, uint32_t a_mn = 0,
+                                                       uint32_t b_mn = 0) {
   return (1u << 4)            // c_format = F32
          | (2u << 7)          // a_format = TF32
          | (2u << 10)         // b_format = TF32
-         | (0u << 15)         // a_major = K
-         | (0u << 16)         // b_major = K
+         | (a_mn << 15)       // a_major
+         | (b_mn << 16)       // b_major
          | ((N >> 3) << 17)   // n_dim
          | ((M >> 4) << 24);  // m_dim
 }
@@ -160,6 +177,30 @@ __device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, ui
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Whole-warp variants: every lane of a converged warp executes the call with warp-uniform
+// operands and one elected lane issues.  Keeping the issuing code warp-uniform lets the compiler
+// feed UTCHMMA from uniform registers directly; under a per-thread `tid == 0` branch it wraps
+// every MMA in an elect / R2UR.BROADCAST / branch waterfall (~70 cycles per instruction, which
+// made the single issuing thread the bottleneck for 32-cycle MMAs).
+__device__ __forceinline__ uint32_t warp_uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+__device__ __forceinline__ void mma_tf32_ts_elect(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                                  uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(
+          smem_u32(bar))
       : "memory");
 }
 // all previously issued tcgen05.mma of this thread arrive on the mbarrier when they complete

@@ -2,16 +2,24 @@
 // the two pixel-major GEMMs on the 5th-gen tensor cores (sm_100a), 3xTF32 error-compensated:
 //
 //   per tile (8 x 16 halo pixels = one M=128 block, 6 x 14 interior):
-//     TMA      z_in, du, z_out halo tiles (SWIZZLE_128B), all three PREFETCHED one tile ahead
-//              (z_in double-buffered; du / z_out land in the g / y buffers as soon as the
-//              previous tile has released them)                            -> shared
+//     TMA      z_in (SWIZZLE_128B_ATOM_32B), du, z_out (SWIZZLE_128B) halo tiles; du / z_out are
+//              PREFETCHED one tile ahead (they land in the g / y buffers as soon as the previous
+//              tile has released them), z_in is issued at the end of the previous tile and lands
+//              behind the g pass                                            -> shared
 //     g pass   g = gamma*rstd*(du - mean(du) - zhat*mean(du*zhat)) in place  (halo)
-//     convert  a = relu(bn(z_in)) row per thread -> tf32 hi/lo -> TMEM (tcgen05.st)
+//     convert  a = relu(bn(z_in)) row per thread -> tf32 hi/lo -> TMEM (tcgen05.st) for MMA 1,
+//              hi in place over z_in / lo beside it in shared memory for MMA 3, z_in itself parked
+//              in TMEM for the epilogue
 //     MMA 1    y = a W1^T            (recomputed pointwise output; never stored in the forward)
 //     dw-bwd   dy = sum_k W2[k] g[q-d_k], dW2 += y g[q-d_k], db2 += g, db1 += dy   (CUDA cores)
-//     convert  dy rows -> hi/lo -> TMEM
-//     MMA 2    h = dy W1             || overlapped with ||  dW1 += dy^T a  (warp-level 3xTF32 mma.sync)
-//     epilogue du_in = h * [u_in > 0] written once (or accumulated), sum(du_in), sum(du_in*zhat)
+//     convert  dy rows -> hi/lo -> TMEM (A of MMA 2);  dy^T (lane = channel, hi on lanes 0..63,
+//              lo on lanes 64..127, column = pixel) -> TMEM (A of MMA 3)
+//     MMA 2    h = dy W1
+//     MMA 3    dW1_tile = [dy_hi ; dy_lo]^T (a_hi + a_lo): K = the 128 pixels, B = the pixel-major
+//              a tile read as an MN-major operand (SWIZZLE_128B_BASE32B, the only MN-major layout
+//              for 32-bit operands) -- runs under the epilogue
+//     epilogue du_in = h * [u_in > 0] written once (or accumulated), sum(du_in), sum(du_in*zhat);
+//              dW1 += dW1_tile (TMEM -> registers, round-to-nearest fp32 adds)
 //
 // Persistent CTAs (1 per SM); parameter gradients and statistics live in registers across all
 // tiles and are flushed once.  Same math as unit_bwd_kernel (kernels_bwd.cu), which stays the
@@ -33,12 +41,16 @@ constexpr int C64 = 64;
 constexpr int HR = 8, HC = 16;          // halo tile rows / cols  (128 pixels = TMEM lanes)
 constexpr int IR = HR - 2, IC = HC - 2; // 6 x 14 interior
 constexpr uint32_t TILE_BYTES = 128 * C64 * 4;   // 32 KB
-constexpr uint32_t TMEM_COLS = 256;
+constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t COL_D1 = 0, COL_D2 = 64, COL_AHI = 128, COL_ALO = 192;
+constexpr uint32_t COL_Z = 256;      // z_in rows (MODE 0), read back by the epilogue
+constexpr uint32_t COL_DYT = 320;    // dy^T, 128 pixel columns
+constexpr uint32_t COL_DW = 448;     // per-tile dW1: lanes 0..63 dy_hi^T a, lanes 64..127 dy_lo^T a
 
 struct Off {
-  static constexpr uint32_t RAW = 0;                       // 2 x z_in tile (TMA, 2 k-blocks of 16 KB)
-  static constexpr uint32_t G = RAW + 2 * TILE_BYTES;      // du (TMA) -> g halo tile, TMA layout
+  static constexpr uint32_t RAW = 0;                       // z_in tile (TMA, 2 ch-blocks of 16 KB) -> a_hi
+  static constexpr uint32_t AL = RAW + TILE_BYTES;         // a_lo (same layout); h tile in MODE 1/2
+  static constexpr uint32_t G = AL + TILE_BYTES;           // du (TMA) -> g halo tile, TMA layout
   static constexpr uint32_t Y = G + TILE_BYTES;            // z_out (TMA) -> y -> dy tile [128][64] swizzled
   static constexpr uint32_t B1HI = Y + TILE_BYTES;         // W1 hi  [co][ci] K-major SW128
   static constexpr uint32_t B1LO = B1HI + 16384;
@@ -63,17 +75,23 @@ __device__ __forceinline__ const float* rchunk(const unsigned char* raw, int pix
                                         (((chunk & 7) ^ (pix & 7)) << 4));
 }
 
-// warp-level m16n8k8 TF32 MMA (registers in / out): used for the small weight-gradient GEMM whose
-// K dimension is the pixel axis (both operands would need a transposed shared-memory copy for
-// tcgen05, which the prefetch buffers leave no room for)
-__device__ __forceinline__ void mma_m16n8k8_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0,
-                                                 uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
-      "{%0,%1,%2,%3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+// byte offset of a 16-byte chunk inside the z_in / a tiles: [ch block][128 pixels][128 B] with the
+// 32-byte halves of a row XOR-swizzled by (pixel & 3)  (TMA SWIZZLE_128B_ATOM_32B == UMMA
+// SWIZZLE_128B_BASE32B, so the tile doubles as the MN-major B operand of the dW1 GEMM)
+__device__ __forceinline__ uint32_t zoff(int pix, int chunk) {
+  return (uint32_t)((chunk >> 3) * 16384 + pix * 128 +
+                    (((((chunk & 7) >> 1) ^ (pix & 3)) << 5) | ((chunk & 1) << 4)));
 }
+
+// Optional per-phase cycle counters (make TIMING=1): thread 0 of CTA 0 adds the clock64() deltas of
+// the 80x80 plain units to status[32 + phase]; read with tools/phase_timing.py.
+#ifdef YUNET_PHASE_TIMING
+#define PT_DECL long long pt_t0 = clock64(); const bool pt_on = (blockIdx.x == 0 && threadIdx.x == 0 && MODE == 0 && a.H >= 80);
+#define PT(k) do { if (pt_on) { const long long t_ = clock64(); atomicAdd(status + 32 + (k), (int)(t_ - pt_t0)); pt_t0 = t_; } } while (0)
+#else
+#define PT_DECL
+#define PT(k)
+#endif
 
 struct Coef4 { float scale, shift, mean, rstd; };
 __device__ __forceinline__ Coef4 bn_coef_tc(const BnRef& r, int c) {
@@ -95,7 +113,9 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(
       (reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-  unsigned char* raw0 = smem + Off::RAW;
+  unsigned char* raw = smem + Off::RAW;               // MODE 0: z_in -> a_hi; else activated a -> a_hi
+  unsigned char* sAL = smem + Off::AL;               // a_lo
+  unsigned char* sH = smem + Off::AL;                // MODE 1/2: h tile for the routing pass
   unsigned char* sG = smem + Off::G;
   unsigned char* sY = smem + Off::Y;
   float* sW2 = reinterpret_cast<float*>(smem + Off::W2);
@@ -103,11 +123,12 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
   float* sCa = reinterpret_cast<float*>(smem + Off::CA);
   float* sCb = reinterpret_cast<float*>(smem + Off::CB);
   float* sCo = reinterpret_cast<float*>(smem + Off::CO);
-  // [0],[3] z_in buffer 0/1, [1] mma1, [2] mma2, [4] du, [5] z_out
+  // [0] z_in, [1] mma1, [2] mma2, [3] mma3 (dW1), [4] du, [5] z_out: one completion per tile each
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Off::BAR);
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 6);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int warp_u = (int)warp_uniform((uint32_t)warp);      // provably warp-uniform copy
   const int quarter = warp & 3;      // TMEM lane quarter
   const int half = warp >> 2;        // which 32 of the 64 channels this warp converts / reads back
   const int row = quarter * 32 + lane;   // pixel of the tile == TMEM lane
@@ -149,9 +170,10 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tbase = *tmem_ptr;
+  const uint32_t tbase = warp_uniform(*tmem_ptr);
   const uint32_t lane_addr = tbase + ((uint32_t)(quarter * 32) << 16);
   constexpr uint32_t idesc = make_idesc_tf32(128, 64);
+  constexpr uint32_t idesc_dw = make_idesc_tf32(128, 64, 0, 1);     // B MN-major
 
   // ---- persistent accumulators
   // depthwise stage: thread -> (channel quad, interior column), marches the 6 interior rows
@@ -160,19 +182,20 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
 #pragma unroll
   for (int k = 0; k < 9; ++k) gw2[k] = make_float4(0.f, 0.f, 0.f, 0.f);
   float4 gb2 = make_float4(0.f, 0.f, 0.f, 0.f), gb1 = gb2;
-  // dW1 (64 co x 64 ci) as warp-level MMA tiles: warp -> 16 co x 32 ci = four m16n8 accumulators
-  const int co0 = (warp & 3) * 16, ci0 = (warp >> 2) * 32;
-  const int fr = lane >> 2, fc = lane & 3;          // fragment row / column ids
-  float gw1[4][4];
+  // dW1: thread (TMEM lane `row`, column half) accumulates row (row & 63) of dW1, input channels
+  // half*32 .. +31; lanes 64..127 carry the dy_lo part of the same rows
+  float gw1[32];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) gw1[i][j] = 0.f;
-  float scj[4], shj[4];                              // BN of the four ci this thread loads
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    scj[j] = (MODE == 0) ? sCa[ci0 + 8 * j + fr] : 1.0f;      // pooled / up-add tiles hold the
-    shj[j] = (MODE == 0) ? sCa[64 + ci0 + 8 * j + fr] : 0.0f;  // activation already (a >= 0)
+  for (int j = 0; j < 32; ++j) gw1[j] = 0.f;
+  // g pass: the channel quad of a thread is fixed (256 % 16 == 0): coefficients in registers
+  const float4 cgs = *reinterpret_cast<const float4*>(sCo + (tid & 15) * 4);
+  const float4 cm1 = *reinterpret_cast<const float4*>(sCo + 64 + (tid & 15) * 4);
+  const float4 cmu = *reinterpret_cast<const float4*>(sCo + 192 + (tid & 15) * 4);
+  float4 ck;                                          // rstd * mean(du * zhat)
+  {
+    const float4 m2 = *reinterpret_cast<const float4*>(sCo + 128 + (tid & 15) * 4);
+    const float4 rs = *reinterpret_cast<const float4*>(sCo + 256 + (tid & 15) * 4);
+    ck = make_float4(rs.x * m2.x, rs.y * m2.y, rs.z * m2.z, rs.w * m2.w);
   }
   // pooled / up-add routing: thread -> (channel quad eq, pixels tid/16 + 16k)
   const int eq = tid & 15;
@@ -198,7 +221,7 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     tma_load_4d(dst + 16384, m, bar, 32, x0_ - 1, y0_ - 1, b_);
   };
   if (tid == 0 && (int)blockIdx.x < ntiles) {
-    if (MODE == 0) issue(&tmap, raw0, &bars[0], blockIdx.x);
+    if (MODE == 0) issue(&tmap, raw, &bars[0], blockIdx.x);
     issue(&tmap_du, sG, &bars[4], blockIdx.x);
     issue(&tmap_zo, sY, &bars[5], blockIdx.x);
   }
@@ -207,14 +230,10 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     int x0, y0, b;
     tile_xyb(tile, x0, y0, b);          // interior origin; halo origin = (x0-1, y0-1)
     const long long img_off = (long long)b * a.H * a.W * C64;
-    const int buf = (MODE == 0) ? (int)(it & 1) : 0;
-    unsigned char* raw = raw0 + buf * TILE_BYTES;      // MODE 0: z_in; else: activated operand a
-    unsigned char* sH = raw0 + TILE_BYTES;             // MODE 1/2: h tile for the routing pass
     const int next = tile + gridDim.x;
+    PT_DECL
 
-    // ---- T0: prefetch the next tile's z_in; turn the prefetched du / z_out tiles into g
-    if (MODE == 0 && tid == 0 && next < ntiles)
-      issue(&tmap, raw0 + (buf ^ 1) * TILE_BYTES, &bars[buf == 0 ? 3 : 0], next);
+    // ---- T0: stage the operand (MODE 1/2); turn the prefetched du / z_out tiles into g
     const float* za_img = a.za + (long long)b * a.H * a.W * C64 * (MODE == 1 ? 4 : 1);
     if (MODE != 0) {
       // pooled / up-added operand a: vector loads (latency overlaps the waits on du / z_out)
@@ -251,11 +270,12 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
             v.w = fmaxf(fmaf(z.w, sc.w, sh.w), 0.f) + fmaxf(fmaf(zb.w, scb.w, shb.w), 0.f);
           }
         }
-        *reinterpret_cast<float4*>(const_cast<float*>(rchunk(raw, pix, ch))) = v;
+        *reinterpret_cast<float4*>(raw + zoff(pix, ch)) = v;
       }
     }
     if (!mbar_wait(&bars[4], ph)) { alive = false; if (lane == 0) atomicExch(status, 14); }
     if (alive && !mbar_wait(&bars[5], ph)) { alive = false; if (lane == 0) atomicExch(status, 15); }
+    PT(0);
     if (alive) {
 #pragma unroll 4
       for (int k = 0; k < 128 * 16 / NT; ++k) {
@@ -267,56 +287,62 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) {
           const float4 d = *reinterpret_cast<const float4*>(gp);
           const float4 z = *reinterpret_cast<const float4*>(rchunk(sY, pix, ch));
-          const float4 gs = *reinterpret_cast<const float4*>(sCo + ch * 4);
-          const float4 m1 = *reinterpret_cast<const float4*>(sCo + 64 + ch * 4);
-          const float4 m2 = *reinterpret_cast<const float4*>(sCo + 128 + ch * 4);
-          const float4 mu = *reinterpret_cast<const float4*>(sCo + 192 + ch * 4);
-          const float4 rs = *reinterpret_cast<const float4*>(sCo + 256 + ch * 4);
-          g.x = gs.x * (d.x - m1.x - (z.x - mu.x) * rs.x * m2.x);
-          g.y = gs.y * (d.y - m1.y - (z.y - mu.y) * rs.y * m2.y);
-          g.z = gs.z * (d.z - m1.z - (z.z - mu.z) * rs.z * m2.z);
-          g.w = gs.w * (d.w - m1.w - (z.w - mu.w) * rs.w * m2.w);
+          g.x = cgs.x * (d.x - cm1.x - (z.x - cmu.x) * ck.x);
+          g.y = cgs.y * (d.y - cm1.y - (z.y - cmu.y) * ck.y);
+          g.z = cgs.z * (d.z - cm1.z - (z.z - cmu.z) * ck.z);
+          g.w = cgs.w * (d.w - cm1.w - (z.w - cmu.w) * ck.w);
         }
         *reinterpret_cast<float4*>(gp) = g;
       }
     }
+    PT(1);
     if (MODE == 0) {
-      if (alive && !mbar_wait(&bars[buf == 0 ? 0 : 3], (it >> 1) & 1)) { alive = false; if (lane == 0) atomicExch(status, 11); }
+      if (alive && !mbar_wait(&bars[0], ph)) { alive = false; if (lane == 0) atomicExch(status, 11); }
     } else {
       __syncthreads();      // operand a staged by all threads
     }
+    PT(2);
 
-    // ---- T1: a = relu(bn(z_in)) row per thread (32 channels per warp half) -> hi/lo -> TMEM
+    // ---- T1: a = relu(bn(z_in)) row per thread (32 channels per warp half) -> hi/lo -> TMEM (A of
+    // MMA 1) and -> shared (hi in place, lo beside it: B of MMA 3); z_in itself -> TMEM
     const int hy = row / HC, hx = row % HC;
     const int gy_r = y0 - 1 + hy, gx_r = x0 - 1 + hx;
     const bool interior = hy >= 1 && hy <= IR && hx >= 1 && hx <= IC && gy_r < a.H && gx_r < a.W;
     if (alive) {
 #pragma unroll
       for (int g16 = 0; g16 < 2; ++g16) {
-        uint32_t hi[16], lo[16];
+        uint32_t hi[16], lo[16], zr[16];
 #pragma unroll
         for (int c4 = 0; c4 < 4; ++c4) {
           const int ch = half * 8 + g16 * 4 + c4;
-          const float4 z = *reinterpret_cast<const float4*>(rchunk(raw, row, ch));
-          const float4 sc = *reinterpret_cast<const float4*>(sCa + ch * 4);
-          const float4 sh = *reinterpret_cast<const float4*>(sCa + 64 + ch * 4);
+          const uint32_t zo = zoff(row, ch);
+          const float4 z = *reinterpret_cast<const float4*>(raw + zo);
           float v[4] = {z.x, z.y, z.z, z.w};
           if (MODE == 0) {
+            const float4 sc = *reinterpret_cast<const float4*>(sCa + ch * 4);
+            const float4 sh = *reinterpret_cast<const float4*>(sCa + 64 + ch * 4);
+            zr[c4 * 4 + 0] = __float_as_uint(z.x); zr[c4 * 4 + 1] = __float_as_uint(z.y);
+            zr[c4 * 4 + 2] = __float_as_uint(z.z); zr[c4 * 4 + 3] = __float_as_uint(z.w);
             v[0] = fmaxf(fmaf(z.x, sc.x, sh.x), 0.f); v[1] = fmaxf(fmaf(z.y, sc.y, sh.y), 0.f);
             v[2] = fmaxf(fmaf(z.z, sc.z, sh.z), 0.f); v[3] = fmaxf(fmaf(z.w, sc.w, sh.w), 0.f);
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j) { hi[c4 * 4 + j] = tf32_hi(v[j]); lo[c4 * 4 + j] = tf32_lo(v[j]); }
+          *reinterpret_cast<uint4*>(raw + zo) = make_uint4(hi[c4 * 4], hi[c4 * 4 + 1], hi[c4 * 4 + 2], hi[c4 * 4 + 3]);
+          *reinterpret_cast<uint4*>(sAL + zo) = make_uint4(lo[c4 * 4], lo[c4 * 4 + 1], lo[c4 * 4 + 2], lo[c4 * 4 + 3]);
         }
         tmem_st16(lane_addr + COL_AHI + half * 32 + g16 * 16, hi);
         tmem_st16(lane_addr + COL_ALO + half * 32 + g16 * 16, lo);
+        if (MODE == 0) tmem_st16(lane_addr + COL_Z + half * 32 + g16 * 16, zr);
       }
       tmem_wait_st();
     }
+    fence_proxy_async_smem();      // a_hi / a_lo (generic writes) are read by MMA 3 (async proxy)
     tc_fence_before();
     __syncthreads();
+    PT(3);
     // ---- T2: MMA 1   D1 = a W1^T
-    if (tid == 0 && alive) {
+    if (warp_u == 0 && __all_sync(0xffffffffu, alive)) {      // whole warp, one elected lane issues
       tc_fence_after();
       const uint32_t bhi = smem_u32(smem + Off::B1HI), blo = smem_u32(smem + Off::B1LO);
       uint32_t acc = 0;
@@ -325,14 +351,15 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const uint32_t koff = (k >> 2) * 8192 + (k & 3) * 32;
-          mma_tf32_ts(tbase + COL_D1, tbase + (pass == 0 ? COL_ALO : COL_AHI) + k * 8,
-                      make_desc_sw128_kmajor((pass == 1 ? blo : bhi) + koff), idesc, acc);
+          mma_tf32_ts_elect(tbase + COL_D1, tbase + (pass == 0 ? COL_ALO : COL_AHI) + k * 8,
+                            make_desc_sw128_kmajor((pass == 1 ? blo : bhi) + koff), idesc, acc);
           acc = 1;
         }
-      mma_commit(&bars[1]);
+      mma_commit_elect(&bars[1]);
     }
     if (alive && !mbar_wait(&bars[1], ph)) { alive = false; if (lane == 0) atomicExch(status, 12); }
     tc_fence_after();
+    PT(4);
     // ---- T3: y (+bias) for interior in-image pixels, exact 0 elsewhere -> sY
     if (alive) {
 #pragma unroll
@@ -355,6 +382,7 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     }
     tc_fence_before();
     __syncthreads();
+    PT(5);
 
     // ---- T4: depthwise backward on the interior: dy in place over y, dW2, db2, db1
     if (alive && dx < IC) {
@@ -406,6 +434,7 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     fence_proxy_async_smem();      // generic writes to the g buffer precede its TMA refill
     __syncthreads();
     if (tid == 0 && next < ntiles && alive) issue(&tmap_du, sG, &bars[4], next);
+    PT(6);
 
     // ---- T5: dy rows -> hi/lo -> TMEM (A columns are free: MMA 1 completed)
     if (alive) {
@@ -424,12 +453,33 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         tmem_st16(lane_addr + COL_AHI + half * 32 + g16 * 16, hi);
         tmem_st16(lane_addr + COL_ALO + half * 32 + g16 * 16, lo);
       }
+      // dy^T for MMA 3: this thread's TMEM lane is output channel (row & 63), hi part on lanes
+      // 0..63 and lo part on lanes 64..127; its warp half covers 64 of the 128 pixel columns.
+      // A warp reads 32 consecutive channels of one pixel per load: conflict-free.
+      {
+        const int m = row & 63;
+        const bool islo = row >= 64;
+        const unsigned char* ybase = sY + half * 64 * 256 + (m & 3) * 4;
+        const int c16 = m >> 2;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint32_t v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float x = *reinterpret_cast<const float*>(ybase + (g * 16 + j) * 256 + ((c16 ^ (j & 7)) << 4));
+            v[j] = islo ? tf32_lo(x) : tf32_hi(x);
+          }
+          tmem_st16(lane_addr + COL_DYT + half * 64 + g * 16, v);
+        }
+      }
       tmem_wait_st();
     }
+    fence_proxy_async_smem();      // y / dy (generic accesses) precede the TMA refill of that buffer
     tc_fence_before();
     __syncthreads();
+    PT(7);
     // ---- T6: MMA 2   D2 = dy W1   (async) ...
-    if (tid == 0 && alive) {
+    if (warp_u == 0 && __all_sync(0xffffffffu, alive)) {
       tc_fence_after();
       const uint32_t bhi = smem_u32(smem + Off::B2HI), blo = smem_u32(smem + Off::B2LO);
       uint32_t acc = 0;
@@ -438,64 +488,48 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const uint32_t koff = (k >> 2) * 8192 + (k & 3) * 32;
-          mma_tf32_ts(tbase + COL_D2, tbase + (pass == 0 ? COL_ALO : COL_AHI) + k * 8,
-                      make_desc_sw128_kmajor((pass == 1 ? blo : bhi) + koff), idesc, acc);
+          mma_tf32_ts_elect(tbase + COL_D2, tbase + (pass == 0 ? COL_ALO : COL_AHI) + k * 8,
+                            make_desc_sw128_kmajor((pass == 1 ? blo : bhi) + koff), idesc, acc);
           acc = 1;
         }
-      mma_commit(&bars[2]);
-    }
-    // ---- ... while the warps do  dW1 += dy^T a  (3xTF32 mma.sync, K = pixels; halo pixels carry
-    // dy == 0, so whole 16-pixel rows 1..6 are used: 12 k-steps of 8)
-    if (alive) {
-      // pixel p0 = r*16 + xh*8 + fc has (p0 & 7) == fc and p1 = p0 + 4 has (p1 & 7) == fc ^ 4:
-      // per-thread byte offsets inside a pixel row are loop-invariant
-      const int c0 = co0 + fr, c1 = c0 + 8;
-      const int oa00 = (((c0 >> 2) ^ fc) << 4) + (c0 & 3) * 4, oa01 = (((c1 >> 2) ^ fc) << 4) + (c1 & 3) * 4;
-      const int oa10 = (((c0 >> 2) ^ fc ^ 4) << 4) + (c0 & 3) * 4, oa11 = (((c1 >> 2) ^ fc ^ 4) << 4) + (c1 & 3) * 4;
-      int ob0[4], ob1[4];
+      mma_commit_elect(&bars[2]);
+      // ---- MMA 3: D_dw[128 x 64] = dy^T(stacked hi | lo, TMEM) x a (MN-major smem: a_hi, then a_lo);
+      // K = 128 pixels in 16 steps of 8 rows (1024 B); fresh accumulator every tile (the running
+      // sum is kept in registers with round-to-nearest adds)
+      const uint32_t ahi = smem_u32(raw), alo = smem_u32(sAL);
+      uint32_t accw = 0;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int ci = ci0 + 8 * j + fr, chn = ci >> 2;
-        ob0[j] = (chn >> 3) * 16384 + (((chn & 7) ^ fc) << 4) + (ci & 3) * 4;
-        ob1[j] = (chn >> 3) * 16384 + (((chn & 7) ^ fc ^ 4) << 4) + (ci & 3) * 4;
-      }
-#pragma unroll 1
-      for (int r = 1; r <= IR; ++r) {
+      for (int pass = 0; pass < 2; ++pass)
 #pragma unroll
-        for (int xh = 0; xh < 2; ++xh) {
-          const int p0 = r * HC + xh * 8 + fc, p1 = p0 + 4;
-          const unsigned char* yr0 = sY + p0 * 256;
-          const unsigned char* yr1 = sY + p1 * 256;
-          const unsigned char* zr0 = raw + p0 * 128;
-          const unsigned char* zr1 = raw + p1 * 128;
-          uint32_t ah[4], al[4];
-          {
-            const float d00 = *reinterpret_cast<const float*>(yr0 + oa00), d01 = *reinterpret_cast<const float*>(yr0 + oa01);
-            const float d10 = *reinterpret_cast<const float*>(yr1 + oa10), d11 = *reinterpret_cast<const float*>(yr1 + oa11);
-            ah[0] = tf32_hi(d00); al[0] = tf32_lo(d00);   // a0: (m = fr,     k = fc)
-            ah[1] = tf32_hi(d01); al[1] = tf32_lo(d01);   // a1: (m = fr + 8, k = fc)
-            ah[2] = tf32_hi(d10); al[2] = tf32_lo(d10);   // a2: (m = fr,     k = fc + 4)
-            ah[3] = tf32_hi(d11); al[3] = tf32_lo(d11);   // a3: (m = fr + 8, k = fc + 4)
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float z0 = *reinterpret_cast<const float*>(zr0 + ob0[j]);
-            const float z1 = *reinterpret_cast<const float*>(zr1 + ob1[j]);
-            const float a0 = fmaxf(fmaf(z0, scj[j], shj[j]), 0.f);   // b0: (k = fc,     n = fr)
-            const float a1 = fmaxf(fmaf(z1, scj[j], shj[j]), 0.f);   // b1: (k = fc + 4, n = fr)
-            const uint32_t bh0 = tf32_hi(a0), bl0 = tf32_lo(a0), bh1 = tf32_hi(a1), bl1 = tf32_lo(a1);
-            mma_m16n8k8_tf32(gw1[j], al, bh0, bh1);
-            mma_m16n8k8_tf32(gw1[j], ah, bl0, bl1);
-            mma_m16n8k8_tf32(gw1[j], ah, bh0, bh1);
-          }
+        for (int k = 0; k < 16; ++k) {
+          mma_tf32_ts_elect(tbase + COL_DW, tbase + COL_DYT + k * 8,
+                            make_desc_sw128_mnmajor((pass == 0 ? ahi : alo) + k * 1024, 16384, 512, 1),
+                            idesc_dw, accw);
+          accw = 1;
         }
-      }
+      mma_commit_elect(&bars[3]);
     }
+    // every warp is done reading y / dy (T5): refill that buffer with the next tile's z_out
+    if (tid == 32 && next < ntiles && alive) issue(&tmap_zo, sY, &bars[5], next);
     if (alive && !mbar_wait(&bars[2], ph)) { alive = false; if (lane == 0) atomicExch(status, 13); }
     tc_fence_after();
-    fence_proxy_async_smem();      // y / dy (generic writes) precede the TMA refill of that buffer
-    __syncthreads();               // every warp is done reading dy (dW1 loop)
-    if (tid == 0 && next < ntiles && alive) issue(&tmap_zo, sY, &bars[5], next);
+    PT(8);
+    // dW1 of this tile -> registers (MODE 0 does it after the epilogue, under which MMA 3 runs)
+    auto collect_dw1 = [&]() {
+      if (alive && !mbar_wait(&bars[3], ph)) { alive = false; if (lane == 0) atomicExch(status, 16); }
+      tc_fence_after();
+      if (alive) {
+#pragma unroll
+        for (int g16 = 0; g16 < 2; ++g16) {
+          uint32_t dv[16];
+          tmem_ld16(lane_addr + COL_DW + half * 32 + g16 * 16, dv);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) gw1[g16 * 16 + j] += __uint_as_float(dv[j]);
+        }
+      }
+    };
+    if (MODE != 0) collect_dw1();      // the routing pass stages h in the a_lo buffer
     if (MODE != 0) {
       // ---- T7': h rows -> shared, then route through the max-pool winner / the up-add children
       if (alive) {
@@ -618,15 +652,17 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
       if (alive) {
 #pragma unroll
         for (int g16 = 0; g16 < 2; ++g16) {
-          uint32_t hv[16];
+          uint32_t hv[16], zv[16];
           tmem_ld16(lane_addr + COL_D2 + half * 32 + g16 * 16, hv);
+          tmem_ld16(lane_addr + COL_Z + half * 32 + g16 * 16, zv);
           tmem_wait_ld();
           if (interior) {
             float* dst = a.dua + img_off + ((long long)gy_r * a.W + gx_r) * C64;
 #pragma unroll
             for (int c4 = 0; c4 < 4; ++c4) {
               const int ch = half * 8 + g16 * 4 + c4;
-              const float4 z = *reinterpret_cast<const float4*>(rchunk(raw, row, ch));
+              const float4 z = make_float4(__uint_as_float(zv[c4 * 4]), __uint_as_float(zv[c4 * 4 + 1]),
+                                           __uint_as_float(zv[c4 * 4 + 2]), __uint_as_float(zv[c4 * 4 + 3]));
               const float4 sc = *reinterpret_cast<const float4*>(sCa + ch * 4);
               const float4 sh = *reinterpret_cast<const float4*>(sCa + 64 + ch * 4);
               const float4 mu = *reinterpret_cast<const float4*>(sCa + 128 + ch * 4);
@@ -663,27 +699,37 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
       }
       s1 += (double)v1[0];
       s2 += (double)v2[0];
+      PT(9);
+      collect_dw1();
+      PT(10);
     }
+    // MMA 3 has completed (every thread waited on it): the a_hi / a_lo buffers are free
+    if (MODE == 0 && tid == 0 && next < ntiles && alive) issue(&tmap, raw, &bars[0], next);
     fence_proxy_async_smem();
     tc_fence_before();
     alive = __syncthreads_and(alive ? 1 : 0) != 0;
+    PT(11);
+#ifdef YUNET_PHASE_TIMING
+    if (pt_on) atomicAdd(status + 32 + 15, 1);
+#endif
   }
 
   // ---- flush: parameter gradients -> shared-memory reduction -> one partial vector per CTA
   {
     constexpr int NW1 = 64 * 64, NP = NW1 + 11 * 64;
-    float* sRed = reinterpret_cast<float*>(raw0);      // tile buffers are free (no TMA in flight)
+    float* sRed = reinterpret_cast<float*>(raw);       // tile buffers are free (no TMA in flight)
     __syncthreads();
     for (int i = tid; i < NP; i += NT) sRed[i] = 0.f;
     __syncthreads();
-    // accumulator fragment: c0 (m = fr, n = 2 fc), c1 (m, n + 1), c2 (m + 8, n), c3 (m + 8, n + 1)
+    // TMEM lane `row` holds row (row & 63) of dW1 (hi part on lanes < 64, lo part above)
+    if (row < 64) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int co = co0 + fr, ci = ci0 + 8 * j + 2 * fc;
-      sRed[co * 64 + ci] = gw1[j][0];
-      sRed[co * 64 + ci + 1] = gw1[j][1];
-      sRed[(co + 8) * 64 + ci] = gw1[j][2];
-      sRed[(co + 8) * 64 + ci + 1] = gw1[j][3];
+      for (int j = 0; j < 32; ++j) sRed[row * 64 + half * 32 + j] = gw1[j];
+    }
+    __syncthreads();
+    if (row >= 64) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) sRed[(row - 64) * 64 + half * 32 + j] += gw1[j];
     }
     float vals[44];
 #pragma unroll
@@ -767,8 +813,10 @@ cudaError_t launch_unit_bwd_tc(int mode, const UnitBwdArgs& a, int num_sms, int*
     cuuint64_t strides[3] = {256, (cuuint64_t)a.W * 256, (cuuint64_t)a.H * a.W * 256};
     cuuint32_t box[4] = {32, HC, HR, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
+    // z_in lands in the layout MMA 3 reads as an MN-major operand (32-byte swizzle atoms)
     CUresult r = enc(&tm[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base[i]), dims,
-                     strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     i == 0 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
   }

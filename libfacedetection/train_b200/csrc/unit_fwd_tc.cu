@@ -143,7 +143,7 @@ unit_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const UnitFwdArgs a
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tbase = *tmem_ptr;
+  const uint32_t tbase = warp_uniform(*tmem_ptr);
   const uint32_t lane_addr = tbase + ((uint32_t)(quarter * 32) << 16);
   constexpr uint32_t idesc = make_idesc_tf32(128, COUT);
 
@@ -280,7 +280,8 @@ unit_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const UnitFwdArgs a
     tc_fence_before();
     // the four warps of this M block meet, then one thread issues the block's 24 MMAs
     asm volatile("bar.sync %0, 128;" ::"r"(1 + mblk) : "memory");
-    if ((tid & 127) == 0 && alive) {
+    // whole first warp of the M block, one elected lane issues (see tc_common.cuh)
+    if (warp_uniform((uint32_t)(warp & 3)) == 0 && __all_sync(0xffffffffu, alive)) {
       tc_fence_after();
       const uint32_t dcol = tbase + (mblk == 0 ? COL_D0 : COL_D1);
       const uint32_t bhi = smem_u32(sBhi), blo = smem_u32(sBlo);
@@ -292,11 +293,11 @@ unit_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const UnitFwdArgs a
           const uint32_t koff = (k >> 2) * C::B_BLOCK + (k & 3) * 32;
           const uint64_t bd = make_desc_sw128_kmajor((pass == 1 ? blo : bhi) + koff);
           const uint32_t at = tbase + (pass == 0 ? COL_ALO : COL_AHI) + k * 8;
-          mma_tf32_ts(dcol, at, bd, idesc, acc);
+          mma_tf32_ts_elect(dcol, at, bd, idesc, acc);
           acc = 1;
         }
       }
-      mma_commit(&bars[1 + mblk]);
+      mma_commit_elect(&bars[1 + mblk]);
     }
     // ---- epilogue of M block `mblk`: accumulators -> y tile (over the consumed raw block)
     if (alive) {
