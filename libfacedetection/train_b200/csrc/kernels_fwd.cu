@@ -15,6 +15,8 @@
 #include <cstdio>
 
 #include "kernels.h"
+#include "prefetch.cuh"
+#include "f32x2.cuh"
 
 namespace yunet {
 
@@ -54,10 +56,7 @@ __device__ __forceinline__ float4 add4(float4 a, float4 b) {
   return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
 }
 __device__ __forceinline__ void fma4(float4& acc, float4 w, float4 v) {
-  acc.x = fmaf(w.x, v.x, acc.x);
-  acc.y = fmaf(w.y, v.y, acc.y);
-  acc.z = fmaf(w.z, v.z, acc.z);
-  acc.w = fmaf(w.w, v.w, acc.w);
+  fma4p(acc, w, v);
 }
 __device__ __forceinline__ float4 ldg4(const float* p) {
   return __ldg(reinterpret_cast<const float4*>(p));
@@ -144,6 +143,31 @@ __global__ void __launch_bounds__(NT, 2) unit_fwd_kernel(const UnitFwdArgs a) {
   const int b = t / tiles_y;
   const int x0 = tx * C::TW, y0 = ty * C::TH;
 
+  // ---- L2 prefetch of the next tile's input rows (one bulk request per row)
+  {
+    const int nt = tile + gridDim.x;
+    if (nt < ntiles && tid < 96) {
+      int t2 = nt;
+      const int ntx = t2 % tiles_x; t2 /= tiles_x;
+      const int nty = t2 % tiles_y;
+      const int nb = t2 / tiles_y;
+      const int nx0 = ntx * C::TW, ny0 = nty * C::TH;
+      if (MODE == 1) {
+        l2_prefetch_tile<CIN>(a.za + (long long)nb * a.H * a.W * 4 * CIN, a.H * 2, a.W * 2,
+                              (ny0 - 1) * 2, (ny0 + C::TH + 1) * 2, (nx0 - 1) * 2,
+                              (nx0 + C::TW + 1) * 2, tid);
+      } else {
+        if (tid < 64)
+          l2_prefetch_tile<CIN>(a.za + (long long)nb * a.H * a.W * CIN, a.H, a.W, ny0 - 1,
+                                ny0 + C::TH + 1, nx0 - 1, nx0 + C::TW + 1, tid);
+        else if (MODE == 2)
+          l2_prefetch_tile<CIN>(a.zb + (long long)nb * (a.H >> 1) * (a.W >> 1) * CIN, a.H >> 1,
+                                a.W >> 1, (ny0 - 1) >> 1, ((ny0 + C::TH) >> 1) + 1, (nx0 - 1) >> 1,
+                                ((nx0 + C::TW) >> 1) + 1, tid - 64);
+      }
+    }
+  }
+
   // ---- stage 1: halo tile of activated inputs -> sA
   {
     constexpr int Q = CIN / 4;
@@ -215,7 +239,7 @@ __global__ void __launch_bounds__(NT, 2) unit_fwd_kernel(const UnitFwdArgs a) {
       for (int i = 0; i < C::PPT; ++i) {
         const float ak = kk == 0 ? av[i].x : kk == 1 ? av[i].y : kk == 2 ? av[i].z : av[i].w;
 #pragma unroll
-        for (int j = 0; j < C::CPT; ++j) acc[i][j] = fmaf(ak, wv[j], acc[i][j]);
+        for (int j = 0; j < C::CPT; j += 2) fma2(acc[i][j], acc[i][j + 1], ak, ak, wv[j], wv[j + 1]);
       }
     }
   }
@@ -274,8 +298,7 @@ __global__ void __launch_bounds__(NT, 2) unit_fwd_kernel(const UnitFwdArgs a) {
         float* dst = a.zout + (long long)b * a.out_batch_stride + ((long long)gy * a.W + gx) * COUT + dq * 4;
         *reinterpret_cast<float4*>(dst) = o;
         s1 = add4(s1, o);
-        s2.x = fmaf(o.x, o.x, s2.x); s2.y = fmaf(o.y, o.y, s2.y);
-        s2.z = fmaf(o.z, o.z, s2.z); s2.w = fmaf(o.w, o.w, s2.w);
+        fma4p(s2, o, o);
       }
 #pragma unroll
       for (int d = 0; d < 3; ++d) { ra[d] = rb[d]; rb[d] = rc[d]; }
@@ -337,6 +360,25 @@ __global__ void __launch_bounds__(256, 2) stem_fwd_kernel(const StemArgs a) {
     const int b = t / tiles_y;
     const int ox0 = tx * ST_TW, oy0 = ty * ST_TH;
     const int ix0 = 2 * ox0 - 1, iy0 = 2 * oy0 - 1;
+    {   // L2 prefetch of the next tile's image rows (3 planes, 128-byte lines)
+      const int nt = tile + gridDim.x;
+      if (nt < ntiles) {
+        int t2 = nt;
+        const int ntx = t2 % tiles_x; t2 /= tiles_x;
+        const int nty = t2 % tiles_y;
+        const int nb = t2 / tiles_y;
+        const int nix0 = 2 * ntx * ST_TW - 1, niy0 = 2 * nty * ST_TH - 1;
+        constexpr int LPR = (ST_IW * 4 + 127) / 128 + 1;
+        for (int i = tid; i < 3 * ST_IH * LPR; i += 256) {
+          const int c = i / (ST_IH * LPR), r = (i / LPR) % ST_IH, l = i % LPR;
+          const int gy = niy0 + r;
+          int gx = nix0 + l * 32;
+          if (gx < 0) gx = 0;
+          if (gy >= 0 && gy < a.Hin && gx < a.Win && gx < nix0 + ST_IW)
+            l2_prefetch_line(a.img + (((long long)nb * 3 + c) * a.Hin + gy) * a.Win + gx);
+        }
+      }
+    }
     __syncthreads();      // previous tile's readers of sIn are done (also covers the weight setup)
 #pragma unroll 4
     for (int i = tid; i < 3 * ST_IH * ST_IW; i += 256) {
@@ -366,14 +408,10 @@ __global__ void __launch_bounds__(256, 2) stem_fwd_kernel(const StemArgs a) {
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
             const float4 w = *reinterpret_cast<const float4*>(&sW[k][j4 * 4]);
-            acc[0][j4 * 4 + 0] = fmaf(v0, w.x, acc[0][j4 * 4 + 0]);
-            acc[0][j4 * 4 + 1] = fmaf(v0, w.y, acc[0][j4 * 4 + 1]);
-            acc[0][j4 * 4 + 2] = fmaf(v0, w.z, acc[0][j4 * 4 + 2]);
-            acc[0][j4 * 4 + 3] = fmaf(v0, w.w, acc[0][j4 * 4 + 3]);
-            acc[1][j4 * 4 + 0] = fmaf(v1, w.x, acc[1][j4 * 4 + 0]);
-            acc[1][j4 * 4 + 1] = fmaf(v1, w.y, acc[1][j4 * 4 + 1]);
-            acc[1][j4 * 4 + 2] = fmaf(v1, w.z, acc[1][j4 * 4 + 2]);
-            acc[1][j4 * 4 + 3] = fmaf(v1, w.w, acc[1][j4 * 4 + 3]);
+            fma2(acc[0][j4 * 4 + 0], acc[0][j4 * 4 + 1], v0, v0, w.x, w.y);
+            fma2(acc[0][j4 * 4 + 2], acc[0][j4 * 4 + 3], v0, v0, w.z, w.w);
+            fma2(acc[1][j4 * 4 + 0], acc[1][j4 * 4 + 1], v1, v1, w.x, w.y);
+            fma2(acc[1][j4 * 4 + 2], acc[1][j4 * 4 + 3], v1, v1, w.z, w.w);
           }
         }
     float vals[32];

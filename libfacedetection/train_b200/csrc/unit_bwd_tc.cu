@@ -29,6 +29,7 @@
 
 #include "kernels.h"
 #include "tc_common.cuh"
+#include "f32x2.cuh"
 
 namespace yunet {
 
@@ -174,6 +175,14 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
   const uint32_t lane_addr = tbase + ((uint32_t)(quarter * 32) << 16);
   constexpr uint32_t idesc = make_idesc_tf32(128, 64);
   constexpr uint32_t idesc_dw = make_idesc_tf32(128, 64, 0, 1);     // B MN-major
+  // operand descriptors of the buffer bases; a byte offset inside a buffer adds (offset >> 4) to
+  // the start-address field (buffers are 1024-byte aligned and below 256 KB: no carry)
+  const uint64_t dB1hi = make_desc_sw128_kmajor(smem_u32(smem + Off::B1HI));
+  const uint64_t dB1lo = make_desc_sw128_kmajor(smem_u32(smem + Off::B1LO));
+  const uint64_t dB2hi = make_desc_sw128_kmajor(smem_u32(smem + Off::B2HI));
+  const uint64_t dB2lo = make_desc_sw128_kmajor(smem_u32(smem + Off::B2LO));
+  const uint64_t dAhi = make_desc_sw128_mnmajor(smem_u32(smem + Off::RAW), 16384, 512, 1);
+  const uint64_t dAlo = make_desc_sw128_mnmajor(smem_u32(smem + Off::AL), 16384, 512, 1);
 
   // ---- persistent accumulators
   // depthwise stage: thread -> (channel quad, interior column), marches the 6 interior rows
@@ -344,17 +353,15 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     // ---- T2: MMA 1   D1 = a W1^T
     if (warp_u == 0 && __all_sync(0xffffffffu, alive)) {      // whole warp, one elected lane issues
       tc_fence_after();
-      const uint32_t bhi = smem_u32(smem + Off::B1HI), blo = smem_u32(smem + Off::B1LO);
-      uint32_t acc = 0;
+      // two independent accumulation chains (hi*hi -> D1, the two cross terms -> D2, which is
+      // free until MMA 2), interleaved so that dependent MMAs are never back to back
 #pragma unroll
-      for (int pass = 0; pass < 3; ++pass)
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint32_t koff = (k >> 2) * 8192 + (k & 3) * 32;
-          mma_tf32_ts_elect(tbase + COL_D1, tbase + (pass == 0 ? COL_ALO : COL_AHI) + k * 8,
-                            make_desc_sw128_kmajor((pass == 1 ? blo : bhi) + koff), idesc, acc);
-          acc = 1;
-        }
+      for (int k = 0; k < 8; ++k) {
+        const uint32_t koff = ((k >> 2) * 8192 + (k & 3) * 32) >> 4;
+        mma_tf32_ts_elect(tbase + COL_D1, tbase + COL_AHI + k * 8, dB1hi + koff, idesc, k != 0);
+        mma_tf32_ts_elect(tbase + COL_D2, tbase + COL_ALO + k * 8, dB1hi + koff, idesc, k != 0);
+        mma_tf32_ts_elect(tbase + COL_D2, tbase + COL_AHI + k * 8, dB1lo + koff, idesc, 1);
+      }
       mma_commit_elect(&bars[1]);
     }
     if (alive && !mbar_wait(&bars[1], ph)) { alive = false; if (lane == 0) atomicExch(status, 12); }
@@ -364,18 +371,19 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     if (alive) {
 #pragma unroll
       for (int g16 = 0; g16 < 2; ++g16) {
-        uint32_t v[16];
+        uint32_t v[16], vx[16];
         tmem_ld16(lane_addr + COL_D1 + half * 32 + g16 * 16, v);
+        tmem_ld16(lane_addr + COL_D2 + half * 32 + g16 * 16, vx);
         tmem_wait_ld();
 #pragma unroll
         for (int c4 = 0; c4 < 4; ++c4) {
           const int ch = half * 8 + g16 * 4 + c4;
           const float4 bb = *reinterpret_cast<const float4*>(sB1 + ch * 4);
           float4 o;
-          o.x = interior ? __uint_as_float(v[c4 * 4 + 0]) + bb.x : 0.f;
-          o.y = interior ? __uint_as_float(v[c4 * 4 + 1]) + bb.y : 0.f;
-          o.z = interior ? __uint_as_float(v[c4 * 4 + 2]) + bb.z : 0.f;
-          o.w = interior ? __uint_as_float(v[c4 * 4 + 3]) + bb.w : 0.f;
+          o.x = interior ? (__uint_as_float(v[c4 * 4 + 0]) + __uint_as_float(vx[c4 * 4 + 0])) + bb.x : 0.f;
+          o.y = interior ? (__uint_as_float(v[c4 * 4 + 1]) + __uint_as_float(vx[c4 * 4 + 1])) + bb.y : 0.f;
+          o.z = interior ? (__uint_as_float(v[c4 * 4 + 2]) + __uint_as_float(vx[c4 * 4 + 2])) + bb.z : 0.f;
+          o.w = interior ? (__uint_as_float(v[c4 * 4 + 3]) + __uint_as_float(vx[c4 * 4 + 3])) + bb.w : 0.f;
           *reinterpret_cast<float4*>(tchunk(sY, row, ch)) = o;
         }
       }
@@ -416,12 +424,8 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         for (int kx = 0; kx < 3; ++kx) {
           const float4 g0 = rc[2 - kx], g1 = rb[2 - kx], g2 = ra[2 - kx];
           const float4 w0 = w2r[kx], w1 = w2r[3 + kx], w2 = w2r[6 + kx];
-          dy.x = fmaf(w0.x, g0.x, dy.x); dy.y = fmaf(w0.y, g0.y, dy.y); dy.z = fmaf(w0.z, g0.z, dy.z); dy.w = fmaf(w0.w, g0.w, dy.w);
-          dy.x = fmaf(w1.x, g1.x, dy.x); dy.y = fmaf(w1.y, g1.y, dy.y); dy.z = fmaf(w1.z, g1.z, dy.z); dy.w = fmaf(w1.w, g1.w, dy.w);
-          dy.x = fmaf(w2.x, g2.x, dy.x); dy.y = fmaf(w2.y, g2.y, dy.y); dy.z = fmaf(w2.z, g2.z, dy.z); dy.w = fmaf(w2.w, g2.w, dy.w);
-          gw2[kx].x = fmaf(y.x, g0.x, gw2[kx].x); gw2[kx].y = fmaf(y.y, g0.y, gw2[kx].y); gw2[kx].z = fmaf(y.z, g0.z, gw2[kx].z); gw2[kx].w = fmaf(y.w, g0.w, gw2[kx].w);
-          gw2[3 + kx].x = fmaf(y.x, g1.x, gw2[3 + kx].x); gw2[3 + kx].y = fmaf(y.y, g1.y, gw2[3 + kx].y); gw2[3 + kx].z = fmaf(y.z, g1.z, gw2[3 + kx].z); gw2[3 + kx].w = fmaf(y.w, g1.w, gw2[3 + kx].w);
-          gw2[6 + kx].x = fmaf(y.x, g2.x, gw2[6 + kx].x); gw2[6 + kx].y = fmaf(y.y, g2.y, gw2[6 + kx].y); gw2[6 + kx].z = fmaf(y.z, g2.z, gw2[6 + kx].z); gw2[6 + kx].w = fmaf(y.w, g2.w, gw2[6 + kx].w);
+          fma4p(dy, w0, g0); fma4p(dy, w1, g1); fma4p(dy, w2, g2);
+          fma4p(gw2[kx], y, g0); fma4p(gw2[3 + kx], y, g1); fma4p(gw2[6 + kx], y, g2);
         }
         gb2.x += rb[1].x; gb2.y += rb[1].y; gb2.z += rb[1].z; gb2.w += rb[1].w;
         if (!in) dy = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -481,32 +485,25 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     // ---- T6: MMA 2   D2 = dy W1   (async) ...
     if (warp_u == 0 && __all_sync(0xffffffffu, alive)) {
       tc_fence_after();
-      const uint32_t bhi = smem_u32(smem + Off::B2HI), blo = smem_u32(smem + Off::B2LO);
-      uint32_t acc = 0;
+      // hi*hi -> D2, cross terms -> D1 (y was consumed in T3), interleaved as in MMA 1
 #pragma unroll
-      for (int pass = 0; pass < 3; ++pass)
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint32_t koff = (k >> 2) * 8192 + (k & 3) * 32;
-          mma_tf32_ts_elect(tbase + COL_D2, tbase + (pass == 0 ? COL_ALO : COL_AHI) + k * 8,
-                            make_desc_sw128_kmajor((pass == 1 ? blo : bhi) + koff), idesc, acc);
-          acc = 1;
-        }
+      for (int k = 0; k < 8; ++k) {
+        const uint32_t koff = ((k >> 2) * 8192 + (k & 3) * 32) >> 4;
+        mma_tf32_ts_elect(tbase + COL_D2, tbase + COL_AHI + k * 8, dB2hi + koff, idesc, k != 0);
+        mma_tf32_ts_elect(tbase + COL_D1, tbase + COL_ALO + k * 8, dB2hi + koff, idesc, k != 0);
+        mma_tf32_ts_elect(tbase + COL_D1, tbase + COL_AHI + k * 8, dB2lo + koff, idesc, 1);
+      }
       mma_commit_elect(&bars[2]);
       // ---- MMA 3: D_dw[128 x 64] = dy^T(stacked hi | lo, TMEM) x a (MN-major smem: a_hi, then a_lo);
       // K = 128 pixels in 16 steps of 8 rows (1024 B); fresh accumulator every tile (the running
       // sum is kept in registers with round-to-nearest adds)
-      const uint32_t ahi = smem_u32(raw), alo = smem_u32(sAL);
-      uint32_t accw = 0;
 #pragma unroll
       for (int pass = 0; pass < 2; ++pass)
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
+        for (int k = 0; k < 16; ++k)
           mma_tf32_ts_elect(tbase + COL_DW, tbase + COL_DYT + k * 8,
-                            make_desc_sw128_mnmajor((pass == 0 ? ahi : alo) + k * 1024, 16384, 512, 1),
-                            idesc_dw, accw);
-          accw = 1;
-        }
+                            (pass == 0 ? dAhi : dAlo) + (uint32_t)(k * 1024 >> 4), idesc_dw,
+                            (pass | k) != 0);
       mma_commit_elect(&bars[3]);
     }
     // every warp is done reading y / dy (T5): refill that buffer with the next tile's z_out
@@ -535,14 +532,17 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
       if (alive) {
 #pragma unroll
         for (int g16 = 0; g16 < 2; ++g16) {
-          uint32_t hv[16];
+          uint32_t hv[16], hx[16];
           tmem_ld16(lane_addr + COL_D2 + half * 32 + g16 * 16, hv);
+          tmem_ld16(lane_addr + COL_D1 + half * 32 + g16 * 16, hx);
           tmem_wait_ld();
 #pragma unroll
           for (int c4 = 0; c4 < 4; ++c4)
             *reinterpret_cast<float4*>(tchunk(sH, row, half * 8 + g16 * 4 + c4)) =
-                make_float4(__uint_as_float(hv[c4 * 4]), __uint_as_float(hv[c4 * 4 + 1]),
-                            __uint_as_float(hv[c4 * 4 + 2]), __uint_as_float(hv[c4 * 4 + 3]));
+                make_float4(__uint_as_float(hv[c4 * 4]) + __uint_as_float(hx[c4 * 4]),
+                            __uint_as_float(hv[c4 * 4 + 1]) + __uint_as_float(hx[c4 * 4 + 1]),
+                            __uint_as_float(hv[c4 * 4 + 2]) + __uint_as_float(hx[c4 * 4 + 2]),
+                            __uint_as_float(hv[c4 * 4 + 3]) + __uint_as_float(hx[c4 * 4 + 3]));
         }
       }
       __syncthreads();
@@ -653,9 +653,15 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
 #pragma unroll
         for (int g16 = 0; g16 < 2; ++g16) {
           uint32_t hv[16], zv[16];
-          tmem_ld16(lane_addr + COL_D2 + half * 32 + g16 * 16, hv);
-          tmem_ld16(lane_addr + COL_Z + half * 32 + g16 * 16, zv);
-          tmem_wait_ld();
+          {
+            uint32_t hx[16];
+            tmem_ld16(lane_addr + COL_D2 + half * 32 + g16 * 16, hv);
+            tmem_ld16(lane_addr + COL_D1 + half * 32 + g16 * 16, hx);
+            tmem_ld16(lane_addr + COL_Z + half * 32 + g16 * 16, zv);
+            tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) hv[j] = __float_as_uint(__uint_as_float(hv[j]) + __uint_as_float(hx[j]));
+          }
           if (interior) {
             float* dst = a.dua + img_off + ((long long)gy_r * a.W + gx_r) * C64;
 #pragma unroll

@@ -19,6 +19,7 @@
 
 #include "kernels.h"
 #include "tc_common.cuh"
+#include "f32x2.cuh"
 
 namespace yunet {
 
@@ -284,16 +285,17 @@ unit_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const UnitFwdArgs a
     if (warp_uniform((uint32_t)(warp & 3)) == 0 && __all_sync(0xffffffffu, alive)) {
       tc_fence_after();
       const uint32_t dcol = tbase + (mblk == 0 ? COL_D0 : COL_D1);
-      const uint32_t bhi = smem_u32(sBhi), blo = smem_u32(sBlo);
+      // descriptors of the buffer bases once; an in-buffer byte offset adds (offset >> 4)
+      const uint64_t dbhi = make_desc_sw128_kmajor(smem_u32(sBhi));
+      const uint64_t dblo = make_desc_sw128_kmajor(smem_u32(sBlo));
       uint32_t acc = 0;
 #pragma unroll
       for (int pass = 0; pass < 3; ++pass) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          const uint32_t koff = (k >> 2) * C::B_BLOCK + (k & 3) * 32;
-          const uint64_t bd = make_desc_sw128_kmajor((pass == 1 ? blo : bhi) + koff);
+          const uint32_t koff = ((k >> 2) * C::B_BLOCK + (k & 3) * 32) >> 4;
           const uint32_t at = tbase + (pass == 0 ? COL_ALO : COL_AHI) + k * 8;
-          mma_tf32_ts_elect(dcol, at, bd, idesc, acc);
+          mma_tf32_ts_elect(dcol, at, (pass == 1 ? dblo : dbhi) + koff, idesc, acc);
           acc = 1;
         }
       }
@@ -363,18 +365,12 @@ unit_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const UnitFwdArgs a
           float4 o = bias2;
 #pragma unroll
           for (int d = 0; d < 3; ++d) {
-            o.x = fmaf(w2r[d].x, ra[d].x, o.x); o.y = fmaf(w2r[d].y, ra[d].y, o.y);
-            o.z = fmaf(w2r[d].z, ra[d].z, o.z); o.w = fmaf(w2r[d].w, ra[d].w, o.w);
-            o.x = fmaf(w2r[3 + d].x, rb[d].x, o.x); o.y = fmaf(w2r[3 + d].y, rb[d].y, o.y);
-            o.z = fmaf(w2r[3 + d].z, rb[d].z, o.z); o.w = fmaf(w2r[3 + d].w, rb[d].w, o.w);
-            o.x = fmaf(w2r[6 + d].x, rc[d].x, o.x); o.y = fmaf(w2r[6 + d].y, rc[d].y, o.y);
-            o.z = fmaf(w2r[6 + d].z, rc[d].z, o.z); o.w = fmaf(w2r[6 + d].w, rc[d].w, o.w);
+            fma4p(o, w2r[d], ra[d]); fma4p(o, w2r[3 + d], rb[d]); fma4p(o, w2r[6 + d], rc[d]);
           }
           if (y0 + dr0 + i < a.H && gx < a.W) {
             *reinterpret_cast<float4*>(dst0 + i * dst_rs) = o;
             s1.x += o.x; s1.y += o.y; s1.z += o.z; s1.w += o.w;
-            s2.x = fmaf(o.x, o.x, s2.x); s2.y = fmaf(o.y, o.y, s2.y);
-            s2.z = fmaf(o.z, o.z, s2.z); s2.w = fmaf(o.w, o.w, s2.w);
+            fma4p(s2, o, o);
           }
 #pragma unroll
           for (int d = 0; d < 3; ++d) { ra[d] = rb[d]; rb[d] = rc[d]; }

@@ -23,15 +23,15 @@ torch.cuda.synchronize()
 off = _capi.lib.yunet_ws_offset(eng.h, B, S, S, 1, 0, 3)
 ws = eng.workspace(B, S, S, True)
 st = ws[off:off + 256].view(torch.int32)
-st[32:48] = 0
+st[32:50] = 0
 eng.train_step(img, gt, offs, lr=1e-5)
 torch.cuda.synchronize()
 c = st.cpu().tolist()
 names = ['wait du/z_out', 'g pass', 'wait z_in', 'T1 convert a', 'MMA1 issue+wait', 'T3 y->smem',
          'T4 depthwise', 'T5 dy->TMEM (+T)', 'MMA2/3 issue + wait MMA2', 'epilogue', 'collect dW1',
          'end sync']
-ntile = max(c[47], 1)
-tot = sum(c[32:44])
-print(f'tiles timed {c[47]}  cycles/tile {tot / ntile:.0f}  flags {c[:4]}')
+ntile = max(c[48], 1)
+tot = sum(c[33:45])
+print(f'tiles timed {c[48]}  cycles/tile {tot / ntile:.0f}  flags {c[:4]}')
 for i, n in enumerate(names):
-    print(f'  {n:28s} {c[32 + i] / ntile:8.0f} cyc  {100.0 * c[32 + i] / max(tot, 1):5.1f}%')
+    print(f'  {n:28s} {c[33 + i] / ntile:8.0f} cyc  {100.0 * c[33 + i] / max(tot, 1):5.1f}%')
