@@ -317,9 +317,26 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     const int hy = row / HC, hx = row % HC;
     const int gy_r = y0 - 1 + hy, gx_r = x0 - 1 + hx;
     const bool interior = hy >= 1 && hy <= IR && hx >= 1 && hx <= IC && gy_r < a.H && gx_r < a.W;
-    if (alive) {
+    // The conversion runs in two halves of 16 channels per warp; the MMAs of the k-steps a half
+    // completes ({0,1,4,5}, then {2,3,6,7}) are issued right behind it, so the first 12 MMAs and
+    // their start-up latency run under the second half of the conversion.
+    auto issue_mma1 = [&](int part) {
+      if (warp_u == 0 && __all_sync(0xffffffffu, alive)) {      // whole warp, one elected lane issues
+        tc_fence_after();
 #pragma unroll
-      for (int g16 = 0; g16 < 2; ++g16) {
+        for (int kk = 0; kk < 4; ++kk) {
+          const int k = (kk >> 1) * 4 + part * 2 + (kk & 1);
+          const uint32_t koff = ((k >> 2) * 8192 + (k & 3) * 32) >> 4;
+          mma_tf32_ts_elect(tbase + COL_D1, tbase + COL_ALO + k * 8, dB1hi + koff, idesc, (part | kk) != 0);
+          mma_tf32_ts_elect(tbase + COL_D1, tbase + COL_AHI + k * 8, dB1lo + koff, idesc, 1);
+          mma_tf32_ts_elect(tbase + COL_D1, tbase + COL_AHI + k * 8, dB1hi + koff, idesc, 1);
+        }
+        if (part == 1) mma_commit_elect(&bars[1]);
+      }
+    };
+#pragma unroll
+    for (int g16 = 0; g16 < 2; ++g16) {
+      if (alive) {
         uint32_t hi[16], lo[16], zr[16];
 #pragma unroll
         for (int c4 = 0; c4 < 4; ++c4) {
@@ -343,27 +360,14 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         tmem_st16(lane_addr + COL_AHI + half * 32 + g16 * 16, hi);
         tmem_st16(lane_addr + COL_ALO + half * 32 + g16 * 16, lo);
         if (MODE == 0) tmem_st16(lane_addr + COL_Z + half * 32 + g16 * 16, zr);
+        tmem_wait_st();
       }
-      tmem_wait_st();
+      if (g16 == 1) fence_proxy_async_smem();   // a_hi / a_lo (generic writes) are read by MMA 3
+      tc_fence_before();
+      __syncthreads();
+      issue_mma1(g16);       // ---- T2: MMA 1   D1 = a W1^T
     }
-    fence_proxy_async_smem();      // a_hi / a_lo (generic writes) are read by MMA 3 (async proxy)
-    tc_fence_before();
-    __syncthreads();
     PT(3);
-    // ---- T2: MMA 1   D1 = a W1^T
-    if (warp_u == 0 && __all_sync(0xffffffffu, alive)) {      // whole warp, one elected lane issues
-      tc_fence_after();
-      // two independent accumulation chains (hi*hi -> D1, the two cross terms -> D2, which is
-      // free until MMA 2), interleaved so that dependent MMAs are never back to back
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const uint32_t koff = ((k >> 2) * 8192 + (k & 3) * 32) >> 4;
-        mma_tf32_ts_elect(tbase + COL_D1, tbase + COL_AHI + k * 8, dB1hi + koff, idesc, k != 0);
-        mma_tf32_ts_elect(tbase + COL_D2, tbase + COL_ALO + k * 8, dB1hi + koff, idesc, k != 0);
-        mma_tf32_ts_elect(tbase + COL_D2, tbase + COL_AHI + k * 8, dB1lo + koff, idesc, 1);
-      }
-      mma_commit_elect(&bars[1]);
-    }
     if (alive && !mbar_wait(&bars[1], ph)) { alive = false; if (lane == 0) atomicExch(status, 12); }
     tc_fence_after();
     PT(4);
@@ -371,19 +375,18 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     if (alive) {
 #pragma unroll
       for (int g16 = 0; g16 < 2; ++g16) {
-        uint32_t v[16], vx[16];
+        uint32_t v[16];
         tmem_ld16(lane_addr + COL_D1 + half * 32 + g16 * 16, v);
-        tmem_ld16(lane_addr + COL_D2 + half * 32 + g16 * 16, vx);
         tmem_wait_ld();
 #pragma unroll
         for (int c4 = 0; c4 < 4; ++c4) {
           const int ch = half * 8 + g16 * 4 + c4;
           const float4 bb = *reinterpret_cast<const float4*>(sB1 + ch * 4);
           float4 o;
-          o.x = interior ? (__uint_as_float(v[c4 * 4 + 0]) + __uint_as_float(vx[c4 * 4 + 0])) + bb.x : 0.f;
-          o.y = interior ? (__uint_as_float(v[c4 * 4 + 1]) + __uint_as_float(vx[c4 * 4 + 1])) + bb.y : 0.f;
-          o.z = interior ? (__uint_as_float(v[c4 * 4 + 2]) + __uint_as_float(vx[c4 * 4 + 2])) + bb.z : 0.f;
-          o.w = interior ? (__uint_as_float(v[c4 * 4 + 3]) + __uint_as_float(vx[c4 * 4 + 3])) + bb.w : 0.f;
+          o.x = interior ? __uint_as_float(v[c4 * 4 + 0]) + bb.x : 0.f;
+          o.y = interior ? __uint_as_float(v[c4 * 4 + 1]) + bb.y : 0.f;
+          o.z = interior ? __uint_as_float(v[c4 * 4 + 2]) + bb.z : 0.f;
+          o.w = interior ? __uint_as_float(v[c4 * 4 + 3]) + bb.w : 0.f;
           *reinterpret_cast<float4*>(tchunk(sY, row, ch)) = o;
         }
       }
@@ -440,23 +443,39 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     if (tid == 0 && next < ntiles && alive) issue(&tmap_du, sG, &bars[4], next);
     PT(6);
 
-    // ---- T5: dy rows -> hi/lo -> TMEM (A columns are free: MMA 1 completed)
-    if (alive) {
+    // ---- T5 / T6: dy rows -> hi/lo -> TMEM (A columns are free: MMA 1 completed), again in two
+    // halves with the MMAs of  D2 = dy W1  issued behind each; the dy^T staging for MMA 3 runs
+    // under the first batch
+    auto issue_mma2 = [&](int part) {
 #pragma unroll
-      for (int g16 = 0; g16 < 2; ++g16) {
-        uint32_t hi[16], lo[16];
-#pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
-          const int ch = half * 8 + g16 * 4 + c4;
-          const float4 v = *reinterpret_cast<const float4*>(tchunk(sY, row, ch));
-          hi[c4 * 4 + 0] = tf32_hi(v.x); lo[c4 * 4 + 0] = tf32_lo(v.x);
-          hi[c4 * 4 + 1] = tf32_hi(v.y); lo[c4 * 4 + 1] = tf32_lo(v.y);
-          hi[c4 * 4 + 2] = tf32_hi(v.z); lo[c4 * 4 + 2] = tf32_lo(v.z);
-          hi[c4 * 4 + 3] = tf32_hi(v.w); lo[c4 * 4 + 3] = tf32_lo(v.w);
-        }
-        tmem_st16(lane_addr + COL_AHI + half * 32 + g16 * 16, hi);
-        tmem_st16(lane_addr + COL_ALO + half * 32 + g16 * 16, lo);
+      for (int kk = 0; kk < 4; ++kk) {
+        const int k = (kk >> 1) * 4 + part * 2 + (kk & 1);
+        const uint32_t koff = ((k >> 2) * 8192 + (k & 3) * 32) >> 4;
+        mma_tf32_ts_elect(tbase + COL_D2, tbase + COL_ALO + k * 8, dB2hi + koff, idesc, (part | kk) != 0);
+        mma_tf32_ts_elect(tbase + COL_D2, tbase + COL_AHI + k * 8, dB2lo + koff, idesc, 1);
+        mma_tf32_ts_elect(tbase + COL_D2, tbase + COL_AHI + k * 8, dB2hi + koff, idesc, 1);
       }
+    };
+    auto convert_dy = [&](int g16) {
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) {
+        const int ch = half * 8 + g16 * 4 + c4;
+        const float4 v = *reinterpret_cast<const float4*>(tchunk(sY, row, ch));
+        hi[c4 * 4 + 0] = tf32_hi(v.x); lo[c4 * 4 + 0] = tf32_lo(v.x);
+        hi[c4 * 4 + 1] = tf32_hi(v.y); lo[c4 * 4 + 1] = tf32_lo(v.y);
+        hi[c4 * 4 + 2] = tf32_hi(v.z); lo[c4 * 4 + 2] = tf32_lo(v.z);
+        hi[c4 * 4 + 3] = tf32_hi(v.w); lo[c4 * 4 + 3] = tf32_lo(v.w);
+      }
+      tmem_st16(lane_addr + COL_AHI + half * 32 + g16 * 16, hi);
+      tmem_st16(lane_addr + COL_ALO + half * 32 + g16 * 16, lo);
+    };
+    if (alive) { convert_dy(0); tmem_wait_st(); }
+    tc_fence_before();
+    __syncthreads();
+    if (warp_u == 0 && __all_sync(0xffffffffu, alive)) { tc_fence_after(); issue_mma2(0); }
+    if (alive) {
+      convert_dy(1);
       // dy^T for MMA 3: this thread's TMEM lane is output channel (row & 63), hi part on lanes
       // 0..63 and lo part on lanes 64..127; its warp half covers 64 of the 128 pixel columns.
       // A warp reads 32 consecutive channels of one pixel per load: conflict-free.
@@ -482,17 +501,9 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     tc_fence_before();
     __syncthreads();
     PT(7);
-    // ---- T6: MMA 2   D2 = dy W1   (async) ...
     if (warp_u == 0 && __all_sync(0xffffffffu, alive)) {
       tc_fence_after();
-      // hi*hi -> D2, cross terms -> D1 (y was consumed in T3), interleaved as in MMA 1
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const uint32_t koff = ((k >> 2) * 8192 + (k & 3) * 32) >> 4;
-        mma_tf32_ts_elect(tbase + COL_D2, tbase + COL_AHI + k * 8, dB2hi + koff, idesc, k != 0);
-        mma_tf32_ts_elect(tbase + COL_D1, tbase + COL_ALO + k * 8, dB2hi + koff, idesc, k != 0);
-        mma_tf32_ts_elect(tbase + COL_D1, tbase + COL_AHI + k * 8, dB2lo + koff, idesc, 1);
-      }
+      issue_mma2(1);
       mma_commit_elect(&bars[2]);
       // ---- MMA 3: D_dw[128 x 64] = dy^T(stacked hi | lo, TMEM) x a (MN-major smem: a_hi, then a_lo);
       // K = 128 pixels in 16 steps of 8 rows (1024 B); fresh accumulator every tile (the running
@@ -532,17 +543,14 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
       if (alive) {
 #pragma unroll
         for (int g16 = 0; g16 < 2; ++g16) {
-          uint32_t hv[16], hx[16];
+          uint32_t hv[16];
           tmem_ld16(lane_addr + COL_D2 + half * 32 + g16 * 16, hv);
-          tmem_ld16(lane_addr + COL_D1 + half * 32 + g16 * 16, hx);
           tmem_wait_ld();
 #pragma unroll
           for (int c4 = 0; c4 < 4; ++c4)
             *reinterpret_cast<float4*>(tchunk(sH, row, half * 8 + g16 * 4 + c4)) =
-                make_float4(__uint_as_float(hv[c4 * 4]) + __uint_as_float(hx[c4 * 4]),
-                            __uint_as_float(hv[c4 * 4 + 1]) + __uint_as_float(hx[c4 * 4 + 1]),
-                            __uint_as_float(hv[c4 * 4 + 2]) + __uint_as_float(hx[c4 * 4 + 2]),
-                            __uint_as_float(hv[c4 * 4 + 3]) + __uint_as_float(hx[c4 * 4 + 3]));
+                make_float4(__uint_as_float(hv[c4 * 4]), __uint_as_float(hv[c4 * 4 + 1]),
+                            __uint_as_float(hv[c4 * 4 + 2]), __uint_as_float(hv[c4 * 4 + 3]));
         }
       }
       __syncthreads();
@@ -653,15 +661,9 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
 #pragma unroll
         for (int g16 = 0; g16 < 2; ++g16) {
           uint32_t hv[16], zv[16];
-          {
-            uint32_t hx[16];
-            tmem_ld16(lane_addr + COL_D2 + half * 32 + g16 * 16, hv);
-            tmem_ld16(lane_addr + COL_D1 + half * 32 + g16 * 16, hx);
-            tmem_ld16(lane_addr + COL_Z + half * 32 + g16 * 16, zv);
-            tmem_wait_ld();
-#pragma unroll
-            for (int j = 0; j < 16; ++j) hv[j] = __float_as_uint(__uint_as_float(hv[j]) + __uint_as_float(hx[j]));
-          }
+          tmem_ld16(lane_addr + COL_D2 + half * 32 + g16 * 16, hv);
+          tmem_ld16(lane_addr + COL_Z + half * 32 + g16 * 16, zv);
+          tmem_wait_ld();
           if (interior) {
             float* dst = a.dua + img_off + ((long long)gy_r * a.W + gx_r) * C64;
 #pragma unroll
