@@ -216,28 +216,40 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
   const int ntiles = tiles_x * tiles_y * a.B;
   bool alive = true;
   uint32_t it = 0;
-  auto tile_xyb = [&](int tile_, int& x0_, int& y0_, int& b_) {
-    int t_ = tile_;
-    x0_ = (t_ % tiles_x) * IC; t_ /= tiles_x;
-    y0_ = (t_ % tiles_y) * IR;
-    b_ = t_ / tiles_y;
+  // tile coordinates advance incrementally by gridDim.x tiles (no div / mod in the loop)
+  int tx, ty, tb;
+  {
+    int t_ = blockIdx.x;
+    tx = t_ % tiles_x; t_ /= tiles_x;
+    ty = t_ % tiles_y;
+    tb = t_ / tiles_y;
+  }
+  const int dtx = (int)gridDim.x % tiles_x, dty = ((int)gridDim.x / tiles_x) % tiles_y,
+            dtb = (int)gridDim.x / (tiles_x * tiles_y);
+  auto advance = [&](int& x_, int& y_, int& b_) {
+    x_ += dtx;
+    int cy = 0;
+    if (x_ >= tiles_x) { x_ -= tiles_x; cy = 1; }
+    y_ += dty + cy;
+    int cb = 0;
+    if (y_ >= tiles_y) { y_ -= tiles_y; cb = 1; }
+    b_ += dtb + cb;
   };
-  auto issue = [&](const CUtensorMap* m, unsigned char* dst, uint64_t* bar, int tile_) {
-    int x0_, y0_, b_;
-    tile_xyb(tile_, x0_, y0_, b_);
+  auto issue = [&](const CUtensorMap* m, unsigned char* dst, uint64_t* bar, int tx_, int ty_, int b_) {
     mbar_arrive_expect_tx(bar, TILE_BYTES);
-    tma_load_4d(dst, m, bar, 0, x0_ - 1, y0_ - 1, b_);
-    tma_load_4d(dst + 16384, m, bar, 32, x0_ - 1, y0_ - 1, b_);
+    tma_load_4d(dst, m, bar, 0, tx_ * IC - 1, ty_ * IR - 1, b_);
+    tma_load_4d(dst + 16384, m, bar, 32, tx_ * IC - 1, ty_ * IR - 1, b_);
   };
   if (tid == 0 && (int)blockIdx.x < ntiles) {
-    if (MODE == 0) issue(&tmap, raw, &bars[0], blockIdx.x);
-    issue(&tmap_du, sG, &bars[4], blockIdx.x);
-    issue(&tmap_zo, sY, &bars[5], blockIdx.x);
+    if (MODE == 0) issue(&tmap, raw, &bars[0], tx, ty, tb);
+    issue(&tmap_du, sG, &bars[4], tx, ty, tb);
+    issue(&tmap_zo, sY, &bars[5], tx, ty, tb);
   }
   for (int tile = blockIdx.x; tile < ntiles && alive; tile += gridDim.x, ++it) {
     const uint32_t ph = it & 1;
-    int x0, y0, b;
-    tile_xyb(tile, x0, y0, b);          // interior origin; halo origin = (x0-1, y0-1)
+    const int x0 = tx * IC, y0 = ty * IR, b = tb;      // interior origin; halo origin = (x0-1, y0-1)
+    int ntx = tx, nty = ty, ntb = tb;
+    advance(ntx, nty, ntb);                            // coordinates of this CTA's next tile
     const long long img_off = (long long)b * a.H * a.W * C64;
     const int next = tile + gridDim.x;
     PT_DECL
@@ -338,11 +350,15 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     for (int g16 = 0; g16 < 2; ++g16) {
       if (alive) {
         uint32_t hi[16], lo[16], zr[16];
+        float4 zin[4];       // all four loads before the in-place stores (which may alias for the compiler)
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4)
+          zin[c4] = *reinterpret_cast<const float4*>(raw + zoff(row, half * 8 + g16 * 4 + c4));
 #pragma unroll
         for (int c4 = 0; c4 < 4; ++c4) {
           const int ch = half * 8 + g16 * 4 + c4;
           const uint32_t zo = zoff(row, ch);
-          const float4 z = *reinterpret_cast<const float4*>(raw + zo);
+          const float4 z = zin[c4];
           float v[4] = {z.x, z.y, z.z, z.w};
           if (MODE == 0) {
             const float4 sc = *reinterpret_cast<const float4*>(sCa + ch * 4);
@@ -415,13 +431,21 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         ra[d] = *reinterpret_cast<const float4*>(gcol[d]);
         rb[d] = *reinterpret_cast<const float4*>(gcol[d] + HC * 128);
       }
+      // the next row's loads are issued before the current row's arithmetic and store (the
+      // compiler cannot prove that the dy store does not alias the g tile)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) rc[d] = *reinterpret_cast<const float4*>(gcol[d] + 2 * HC * 128);
+      float4 y = *reinterpret_cast<const float4*>(ycol);
 #pragma unroll
       for (int r = 0; r < IR; ++r) {          // interior row r <-> halo row r+1
+        float4 nrc[3], ny;
+        if (r + 1 < IR) {
 #pragma unroll
-        for (int d = 0; d < 3; ++d)
-          rc[d] = *reinterpret_cast<const float4*>(gcol[d] + (r + 2) * HC * 128);
+          for (int d = 0; d < 3; ++d)
+            nrc[d] = *reinterpret_cast<const float4*>(gcol[d] + (r + 3) * HC * 128);
+          ny = *reinterpret_cast<const float4*>(ycol + (r + 1) * HC * 256);
+        }
         const bool in = (y0 + r) < a.H && (x0 + dx) < a.W;
-        const float4 y = *reinterpret_cast<const float4*>(ycol + r * HC * 256);
         float4 dy = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
@@ -436,11 +460,16 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         *reinterpret_cast<float4*>(ycol + r * HC * 256) = dy;
 #pragma unroll
         for (int d = 0; d < 3; ++d) { ra[d] = rb[d]; rb[d] = rc[d]; }
+        if (r + 1 < IR) {
+#pragma unroll
+          for (int d = 0; d < 3; ++d) rc[d] = nrc[d];
+          y = ny;
+        }
       }
     }
     fence_proxy_async_smem();      // generic writes to the g buffer precede its TMA refill
     __syncthreads();
-    if (tid == 0 && next < ntiles && alive) issue(&tmap_du, sG, &bars[4], next);
+    if (tid == 0 && next < ntiles && alive) issue(&tmap_du, sG, &bars[4], ntx, nty, ntb);
     PT(6);
 
     // ---- T5 / T6: dy rows -> hi/lo -> TMEM (A columns are free: MMA 1 completed), again in two
@@ -481,16 +510,21 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
       // A warp reads 32 consecutive channels of one pixel per load: conflict-free.
       {
         const int m = row & 63;
-        const bool islo = row >= 64;
+        const bool islo = warp_uniform((uint32_t)(quarter >= 2)) != 0;
         const unsigned char* ybase = sY + half * 64 * 256 + (m & 3) * 4;
         const int c16 = m >> 2;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           uint32_t v[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float x = *reinterpret_cast<const float*>(ybase + (g * 16 + j) * 256 + ((c16 ^ (j & 7)) << 4));
-            v[j] = islo ? tf32_lo(x) : tf32_hi(x);
+          for (int j = 0; j < 16; ++j)
+            v[j] = __float_as_uint(*reinterpret_cast<const float*>(ybase + (g * 16 + j) * 256 + ((c16 ^ (j & 7)) << 4)));
+          if (islo) {            // warp-uniform (lane quarters 2, 3)
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = tf32_lo(__uint_as_float(v[j]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] &= 0xFFFFE000u;
           }
           tmem_st16(lane_addr + COL_DYT + half * 64 + g * 16, v);
         }
@@ -518,7 +552,7 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
       mma_commit_elect(&bars[3]);
     }
     // every warp is done reading y / dy (T5): refill that buffer with the next tile's z_out
-    if (tid == 32 && next < ntiles && alive) issue(&tmap_zo, sY, &bars[5], next);
+    if (tid == 32 && next < ntiles && alive) issue(&tmap_zo, sY, &bars[5], ntx, nty, ntb);
     if (alive && !mbar_wait(&bars[2], ph)) { alive = false; if (lane == 0) atomicExch(status, 13); }
     tc_fence_after();
     PT(8);
@@ -712,10 +746,11 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
       PT(10);
     }
     // MMA 3 has completed (every thread waited on it): the a_hi / a_lo buffers are free
-    if (MODE == 0 && tid == 0 && next < ntiles && alive) issue(&tmap, raw, &bars[0], next);
+    if (MODE == 0 && tid == 0 && next < ntiles && alive) issue(&tmap, raw, &bars[0], ntx, nty, ntb);
     fence_proxy_async_smem();
     tc_fence_before();
     alive = __syncthreads_and(alive ? 1 : 0) != 0;
+    tx = ntx; ty = nty; tb = ntb;
     PT(11);
 #ifdef YUNET_PHASE_TIMING
     if (pt_on) atomicAdd(status + 32 + 15, 1);
