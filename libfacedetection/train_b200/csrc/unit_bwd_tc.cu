@@ -503,42 +503,46 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     tc_fence_before();
     __syncthreads();
     if (warp_u == 0 && __all_sync(0xffffffffu, alive)) { tc_fence_after(); issue_mma2(0); }
+    if (alive) { convert_dy(1); tmem_wait_st(); }
+    tc_fence_before();
+    __syncthreads();
+    if (warp_u == 0 && __all_sync(0xffffffffu, alive)) {
+      tc_fence_after();
+      issue_mma2(1);
+      mma_commit_elect(&bars[2]);
+    }
+    PT(7);
+    // dy^T for MMA 3 (staged while the second MMA 2 batch runs): this thread's TMEM lane is output
+    // channel (row & 63), hi part on lanes 0..63 and lo part on lanes 64..127; its warp half covers
+    // 64 of the 128 pixel columns.  A warp reads 32 consecutive channels of one pixel per load:
+    // conflict-free.
     if (alive) {
-      convert_dy(1);
-      // dy^T for MMA 3: this thread's TMEM lane is output channel (row & 63), hi part on lanes
-      // 0..63 and lo part on lanes 64..127; its warp half covers 64 of the 128 pixel columns.
-      // A warp reads 32 consecutive channels of one pixel per load: conflict-free.
-      {
-        const int m = row & 63;
-        const bool islo = warp_uniform((uint32_t)(quarter >= 2)) != 0;
-        const unsigned char* ybase = sY + half * 64 * 256 + (m & 3) * 4;
-        const int c16 = m >> 2;
+      const int m = row & 63;
+      const bool islo = warp_uniform((uint32_t)(quarter >= 2)) != 0;
+      const unsigned char* ybase = sY + half * 64 * 256 + (m & 3) * 4;
+      const int c16 = m >> 2;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint32_t v[16];
+      for (int g = 0; g < 4; ++g) {
+        uint32_t v[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            v[j] = __float_as_uint(*reinterpret_cast<const float*>(ybase + (g * 16 + j) * 256 + ((c16 ^ (j & 7)) << 4)));
-          if (islo) {            // warp-uniform (lane quarters 2, 3)
+        for (int j = 0; j < 16; ++j)
+          v[j] = __float_as_uint(*reinterpret_cast<const float*>(ybase + (g * 16 + j) * 256 + ((c16 ^ (j & 7)) << 4)));
+        if (islo) {            // warp-uniform (lane quarters 2, 3)
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = tf32_lo(__uint_as_float(v[j]));
-          } else {
+          for (int j = 0; j < 16; ++j) v[j] = tf32_lo(__uint_as_float(v[j]));
+        } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] &= 0xFFFFE000u;
-          }
-          tmem_st16(lane_addr + COL_DYT + half * 64 + g * 16, v);
+          for (int j = 0; j < 16; ++j) v[j] &= 0xFFFFE000u;
         }
+        tmem_st16(lane_addr + COL_DYT + half * 64 + g * 16, v);
       }
       tmem_wait_st();
     }
     fence_proxy_async_smem();      // y / dy (generic accesses) precede the TMA refill of that buffer
     tc_fence_before();
     __syncthreads();
-    PT(7);
     if (warp_u == 0 && __all_sync(0xffffffffu, alive)) {
       tc_fence_after();
-      issue_mma2(1);
-      mma_commit_elect(&bars[2]);
       // ---- MMA 3: D_dw[128 x 64] = dy^T(stacked hi | lo, TMEM) x a (MN-major smem: a_hi, then a_lo);
       // K = 128 pixels in 16 steps of 8 rows (1024 B); fresh accumulator every tile (the running
       // sum is kept in registers with round-to-nearest adds)
@@ -551,7 +555,7 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                             (pass | k) != 0);
       mma_commit_elect(&bars[3]);
     }
-    // every warp is done reading y / dy (T5): refill that buffer with the next tile's z_out
+    // every warp is done reading y / dy: refill that buffer with the next tile's z_out
     if (tid == 32 && next < ntiles && alive) issue(&tmap_zo, sY, &bars[5], ntx, nty, ntb);
     if (alive && !mbar_wait(&bars[2], ph)) { alive = false; if (lane == 0) atomicExch(status, 13); }
     tc_fence_after();

@@ -198,6 +198,19 @@ unit_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const UnitFwdArgs a
         if (!mbar_wait(&bars[buf == 0 ? 0 : 3], (it >> 1) & 1)) { alive = false; if (lane == 0) atomicExch(status, 1); }
       } else {
         if (tid == 0 && it > 0) issue_tma(tile, 0);       // tile 0 was issued before the loop
+        // the landing buffer is busy until the end of the tile (the y tile aliases it): pull the
+        // next tile's boxes into L2 now so that its TMA, issued one tile later, is an L2 hit
+        if (tid == 32 && tile + (int)gridDim.x < ntiles) {
+          int t_ = tile + gridDim.x;
+          const int tx_ = t_ % tiles_x; t_ /= tiles_x;
+          const int ty_ = t_ % tiles_y;
+          const int b_ = t_ / tiles_y;
+#pragma unroll
+          for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int kb = 0; kb < 2; ++kb)
+              tma_prefetch_l2_4d(&tmap, kb * 32, tx_ * OT - 1, ty_ * OT - 1 + m * 8, b_);
+        }
         if (!mbar_wait(&bars[0], ph)) { alive = false; if (lane == 0) atomicExch(status, 1); }
       }
     } else {
