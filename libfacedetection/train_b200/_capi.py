@@ -149,7 +149,7 @@ class Ctx:
 
     def __del__(self):
         h = getattr(self, '_h', None)
-        if h:
+        if h and lib is not None:      # module globals may already be gone at interpreter exit
             lib.yunet_ctx_destroy(h)
             self._h = None
 

@@ -75,6 +75,17 @@ class YuNetEngine:
         ws = self.workspace(B, H, W, train)
         return ws[off:off + 256].view(torch.int32).cpu()
 
+    # ------------------------------------------------------------------ export
+    def export_cpp(self):
+        """``facedetectcnn-data.cpp`` text, byte-identical to the reference's ``tools/yunet2cpp.py``."""
+        from . import export
+        return export.cpp_data(self.state_dict(), self.arch)
+
+    def export_onnx(self, height=640, width=640):
+        """Serialized 12-output ONNX model (``tools/yunet2onnx.py`` graph, BatchNorm folded)."""
+        from . import export
+        return export.onnx_model(self.state_dict(), self.arch, height, width)
+
     # ------------------------------------------------------------------ parameters
     def param_views(self, bucket=None):
         bucket = self.params if bucket is None else bucket

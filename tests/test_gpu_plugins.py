@@ -88,3 +88,19 @@ def test_train_step_through_autograd_and_torch_sgd(arch, seed):
             assert _rel(sd[k], g['after/' + k]) < 1e-3, k
         if k.endswith('num_batches_tracked'):
             assert int(sd[k]) == int(g['after/' + k])
+
+
+@pytest.mark.parametrize('arch', ['yunet_n', 'yunet_s'])
+def test_engine_export_round_trip(arch):
+    """Weights loaded into the flat device buckets and exported again give the reference tool's
+    ``facedetectcnn-data.cpp`` byte for byte (golden from oracle/gen_golden_export.py)."""
+    import hashlib
+    import json
+    from libfacedetection.train_b200 import YuNetEngine
+    gold = json.load(open(os.path.join(GOLDEN, 'export_golden.json')))[arch]
+    eng = YuNetEngine(arch)
+    d = np.load(os.path.join(GOLDEN, f'weights_{arch}.npz'))
+    eng.load_state_dict({k: torch.from_numpy(d[k]) for k in d.files}, strict=True)
+    text = eng.export_cpp()
+    assert hashlib.sha256(text.encode()).hexdigest() == gold['sha256']
+    assert len(eng.export_onnx(320, 320)) > 100000
