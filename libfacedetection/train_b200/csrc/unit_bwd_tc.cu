@@ -94,6 +94,20 @@ __device__ __forceinline__ uint32_t zoff(int pix, int chunk) {
 #define PT(k)
 #endif
 
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256), 32-byte aligned
+__device__ __forceinline__ void stg_v8(float* p, const float (&v)[8]) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]),
+               "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void ldg_v8(const float* p, float (&v)[8]) {
+  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]),
+                 "=f"(v[7])
+               : "l"(p)
+               : "memory");
+}
+
 struct Coef4 { float scale, shift, mean, rstd; };
 __device__ __forceinline__ Coef4 bn_coef_tc(const BnRef& r, int c) {
   Coef4 k;
@@ -722,9 +736,23 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
               v1[j] = d.x; v1[j + 1] = d.y; v1[j + 2] = d.z; v1[j + 3] = d.w;
               v2[j] = d.x * ((z.x - mu.x) * rs.x); v2[j + 1] = d.y * ((z.y - mu.y) * rs.y);
               v2[j + 2] = d.z * ((z.z - mu.z) * rs.z); v2[j + 3] = d.w * ((z.w - mu.w) * rs.w);
-              float4* p = reinterpret_cast<float4*>(dst + ch * 4);
-              if (a.acc_a) { const float4 o = *p; d.x += o.x; d.y += o.y; d.z += o.z; d.w += o.w; }
-              *p = d;
+            }
+            // 256-bit accesses: a lane owns a whole pixel row, so every access touches 32 distinct
+            // 128-byte lines; two chunks (one full 32-byte sector) per access halve the line visits
+#pragma unroll
+            for (int c8 = 0; c8 < 2; ++c8) {
+              float* p = dst + (half * 8 + g16 * 4 + c8 * 2) * 4;
+              const int j = g16 * 16 + c8 * 8;
+              float o[8];
+#pragma unroll
+              for (int q = 0; q < 8; ++q) o[q] = v1[j + q];
+              if (a.acc_a) {
+                float r[8];
+                ldg_v8(p, r);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) o[q] += r[q];
+              }
+              stg_v8(p, o);
             }
           }
         }
