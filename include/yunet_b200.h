@@ -162,6 +162,18 @@ int yunet_decode_nms(yunet_ctx* ctx, const float* preds, int B, int H, int W, fl
                      float iou_thr, const float* scale_factors, int max_det, float* dets,
                      float* det_kps, int* det_count, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- input pipeline: RandomSquareCrop + Resize + RandomFlip + Normalize ----------
+ * The pixel work of mmdet/datasets/pipelines/transforms.py:1126-1146 (square crop, outside = 128),
+ * :258-263 (mmcv.imresize, cv2 INTER_LINEAR on float32, keep_ratio=False) and :527-530
+ * (horizontal flip) followed by Normalize(mean 0, std 1) + DefaultFormatBundle, for a ragged batch
+ * of decoded images in ONE launch.  pixels: concatenated uint8 HWC (BGR) images; offsets (B) int64
+ * byte offset of each image; hw (B,2) int32 height, width; crop (B,4) int32 [left, top, size,
+ * flip] in source-image coordinates (left / top may be negative, size may exceed the image);
+ * out: (B,3,S,S) fp32.  The random decisions are made by the caller (host mirror: pipeline.py). */
+int yunet_preprocess_u8(yunet_ctx* ctx, const unsigned char* pixels, const long long* offsets,
+                        const int* hw, const int* crop, int B, int S, float pad_value, float* out,
+                        void* stream);
+
 /* ---- debugging / parity helpers ----------------------------------------------------------------
  * yunet_unit_get describes the fused execution plan (used by the formulation tests and the host
  * mirror).  yunet_read_activation copies an internal NHWC activation (pre-BN output `z` of unit

@@ -76,6 +76,7 @@ def _load():
         'yunet_sgd_step': (ci, [vp, vp, vp, vp, ll, cf, cf, cf, cf, vp]),
         'yunet_nms_workspace_bytes': (cs, [vp, ci, ci, ci]),
         'yunet_decode_nms': (ci, [vp, vp, ci, ci, ci, cf, cf, vp, ci, vp, vp, vp, vp, cs, vp]),
+        'yunet_preprocess_u8': (ci, [vp, vp, vp, vp, vp, ci, ci, cf, vp, vp]),
         'yunet_unit_count': (ci, [vp]),
         'yunet_unit_get': (ci, [vp, ci, P(UnitDesc)]),
         'yunet_read_activation': (ci, [vp, ci, vp, vp, ci, ci, ci, ci, vp, vp, vp]),

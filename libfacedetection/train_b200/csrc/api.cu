@@ -532,6 +532,17 @@ int yunet_decode_nms(yunet_ctx* ctx, const float* preds, int B, int H, int W, fl
                    "decode_nms");
 }
 
+int yunet_preprocess_u8(yunet_ctx* ctx, const unsigned char* pixels, const long long* offsets,
+                        const int* hw, const int* crop, int B, int S, float pad_value, float* out,
+                        void* stream) {
+  if (!ctx || !pixels || !offsets || !hw || !crop || !out) return fail(ctx, -1, "preprocess_u8: null pointer");
+  if (B <= 0 || S <= 0 || S > 4096) return fail(ctx, -2, "preprocess_u8: bad shape");
+  Scope sc(ctx, (cudaStream_t)stream, "preprocess_u8");
+  return cuda_fail(ctx, launch_preprocess_u8(pixels, offsets, hw, crop, B, S, pad_value, out,
+                                             (cudaStream_t)stream),
+                   "preprocess_u8");
+}
+
 long long yunet_launch_count(const yunet_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int yunet_set_option(yunet_ctx* ctx, const char* name, int value) {

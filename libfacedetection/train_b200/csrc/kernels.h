@@ -157,6 +157,8 @@ cudaError_t launch_decode_nms(const LevelGeom& g, const float* preds, int B, flo
                               float* det_kps, int* det_count, void* ws, cudaStream_t s);
 
 // ---- sgd.cu ----
+cudaError_t launch_preprocess_u8(const unsigned char* pixels, const long long* offsets, const int* hw,
+                                 const int* crop, int B, int S, float pad, float* out, cudaStream_t s);
 cudaError_t launch_sgd(float* params, const float* grad, float* mom, long long n, float lr,
                        float momentum, float wd, float grad_scale, cudaStream_t s);
 
