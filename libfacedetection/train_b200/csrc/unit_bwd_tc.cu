@@ -30,6 +30,7 @@
 #include "kernels.h"
 #include "tc_common.cuh"
 #include "f32x2.cuh"
+#include "prefetch.cuh"
 
 namespace yunet {
 
@@ -271,6 +272,21 @@ unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     // ---- T0: stage the operand (MODE 1/2); turn the prefetched du / z_out tiles into g
     const float* za_img = a.za + (long long)b * a.H * a.W * C64 * (MODE == 1 ? 4 : 1);
     if (MODE != 0) {
+      // the operand of the NEXT tile is pulled into L2 now (one bulk request per image row), so
+      // that its loads, issued behind the barrier that ends this tile, do not wait on DRAM
+      if (next < ntiles && warp == 7) {
+        const int nx0 = ntx * IC, ny0 = nty * IR;
+        if (MODE == 1) {
+          l2_prefetch_tile<C64>(a.za + (long long)ntb * a.H * a.W * C64 * 4, a.H * 2, a.W * 2,
+                                (ny0 - 1) * 2, (ny0 - 1 + HR) * 2, (nx0 - 1) * 2, (nx0 - 1 + HC) * 2, lane);
+        } else {
+          l2_prefetch_tile<C64>(a.za + (long long)ntb * a.H * a.W * C64, a.H, a.W, ny0 - 1,
+                                ny0 - 1 + HR, nx0 - 1, nx0 - 1 + HC, lane);
+          l2_prefetch_tile<C64>(a.zb + (long long)ntb * (a.H >> 1) * (a.W >> 1) * C64, a.H >> 1,
+                                a.W >> 1, (ny0 - 1) >> 1, ((ny0 - 1 + HR) >> 1) + 1, (nx0 - 1) >> 1,
+                                ((nx0 - 1 + HC) >> 1) + 1, lane - 16);
+        }
+      }
       // pooled / up-added operand a: vector loads (latency overlaps the waits on du / z_out)
 #pragma unroll 4
       for (int k = 0; k < 128 * 16 / NT; ++k) {

@@ -20,6 +20,7 @@
 #include "kernels.h"
 #include "tc_common.cuh"
 #include "f32x2.cuh"
+#include "prefetch.cuh"
 
 namespace yunet {
 
@@ -214,6 +215,24 @@ unit_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const UnitFwdArgs a
         if (!mbar_wait(&bars[0], ph)) { alive = false; if (lane == 0) atomicExch(status, 1); }
       }
     } else {
+      // next tile's operand rows -> L2 (one bulk request per image row)
+      if (tile + (int)gridDim.x < ntiles && warp == 7) {
+        int t_ = tile + gridDim.x;
+        const int tx_ = t_ % tiles_x; t_ /= tiles_x;
+        const int ty_ = t_ % tiles_y;
+        const int b_ = t_ / tiles_y;
+        const int nx0 = tx_ * OT, ny0 = ty_ * OT;
+        if (MODE == 1) {
+          l2_prefetch_tile<64>(a.za + (long long)b_ * a.H * a.W * 64 * 4, a.H * 2, a.W * 2, (ny0 - 1) * 2,
+                               (ny0 - 1 + HT) * 2, (nx0 - 1) * 2, (nx0 - 1 + HT) * 2, lane);
+        } else {
+          l2_prefetch_tile<64>(a.za + (long long)b_ * a.H * a.W * 64, a.H, a.W, ny0 - 1, ny0 - 1 + HT,
+                               nx0 - 1, nx0 - 1 + HT, lane);
+          l2_prefetch_tile<64>(a.zb + (long long)b_ * (a.H >> 1) * (a.W >> 1) * 64, a.H >> 1, a.W >> 1,
+                               (ny0 - 1) >> 1, ((ny0 - 1 + HT) >> 1) + 1, (nx0 - 1) >> 1,
+                               ((nx0 - 1 + HT) >> 1) + 1, lane - 16);
+        }
+      }
       // ---- pooled / up-added operand: cooperative vector loads, activation applied on the way,
       // written in the layout the TMA would have produced (row = pixel, 16 B chunks ^ (row & 7))
 #pragma unroll 4
