@@ -223,8 +223,7 @@ unit_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const UnitFwdArgs a
         const int b_ = t_ / tiles_y;
         const int nx0 = tx_ * OT, ny0 = ty_ * OT;
         if (MODE == 1) {
-          l2_prefetch_tile<64>(a.za + (long long)b_ * a.H * a.W * 64 * 4, a.H * 2, a.W * 2, (ny0 - 1) * 2,
-                               (ny0 - 1 + HT) * 2, (nx0 - 1) * 2, (nx0 - 1 + HT) * 2, lane);
+          // pooled operand (4x the bytes): measured slower with the prefetch, left to the loads
         } else {
           l2_prefetch_tile<64>(a.za + (long long)b_ * a.H * a.W * 64, a.H, a.W, ny0 - 1, ny0 - 1 + HT,
                                nx0 - 1, nx0 - 1 + HT, lane);
