@@ -176,3 +176,60 @@ def load_wider_gt(gt_dir):
             out[event][name] = dict(boxes=gt_mat['face_bbx_list'][i][0][j][0].astype('float'),
                                     **{s: keep[s][i][0][j][0] for s in SETTINGS})
     return out
+
+
+# --------------------------------------------------------------------------- test-time drivers
+def prepare_test_image(img_u8, mode=0, divisor=32):
+    """Host side of the reference's test pipeline (``configs/yunet_n.py:59-78`` as patched by
+    ``tools/test_widerface.py:76-96``): mode 0 = keep-ratio resize into 640x640, mode > 30 = into
+    (mode, mode), each followed by a zero pad to that size; mode 2 = original size padded to a
+    multiple of ``divisor`` (mode 1, 1100 x 1650, is not supported yet).  Returns the float32 CHW image (BGR, 0..255)
+    and the ``[w_scale, h_scale, w_scale, h_scale]`` float32 factor detections are divided by.
+
+    Resizing uses ``cv2.resize`` on the uint8 image exactly like ``mmcv.imrescale`` (cv2 backend)."""
+    h, w = img_u8.shape[:2]
+    if mode == 1:
+        raise NotImplementedError('mode 1 (1100 x 1650) exceeds the 8 704 priors per image the NMS '
+                                  'kernel keeps in shared memory')
+    if mode == 2:
+        out_h, out_w = -(-h // divisor) * divisor, -(-w // divisor) * divisor
+        img, factor = img_u8, np.ones(4, np.float32)
+    else:
+        side = 640 if mode == 0 else int(mode)
+        scale = min(side / max(h, w), side / min(h, w))                 # mmcv.rescale_size
+        new_w, new_h = int(w * float(scale) + 0.5), int(h * float(scale) + 0.5)
+        import cv2
+        img = cv2.resize(img_u8, (new_w, new_h), interpolation=cv2.INTER_LINEAR)
+        w_scale, h_scale = new_w / w, new_h / h
+        factor = np.array([w_scale, h_scale, w_scale, h_scale], dtype=np.float32)
+        out_h = out_w = -(-side // divisor) * divisor                   # Pad(size=(side, side))
+    chw = np.zeros((3, out_h, out_w), np.float32)
+    chw[:, :img.shape[0], :img.shape[1]] = img.transpose(2, 0, 1)
+    return chw, factor
+
+
+def engine_detector(engine, score_thr=0.02, iou_thr=0.45):
+    """``detect(chw_float32, factor) -> (N,5)`` on the GPU engine (boxes rescaled by ``factor``)."""
+    import torch
+
+    def detect(chw, factor):
+        img = torch.from_numpy(chw).to(engine.device)[None]
+        sf = torch.from_numpy(np.asarray(factor, np.float32)).to(engine.device)[None]
+        dets, counts, _ = engine.detect(img, score_thr, iou_thr, scale_factors=sf)
+        n = int(counts[0])
+        return dets[0, :n].cpu().numpy()
+    return detect
+
+
+def evaluate_wider(detect, samples, gt, mode=0, iou_thresh=0.5):
+    """``samples``: iterable of ``(event, image_name, uint8 BGR image)``; ``detect`` as returned by
+    ``engine_detector``.  Returns ``([AP_easy, AP_medium, AP_hard], results)``."""
+    results = {}
+    for event, name, img in samples:
+        chw, factor = prepare_test_image(img, mode)
+        detections_to_results(results, event, name, detect(chw, factor))
+    for event, images in gt.items():                    # images the detector never saw count as empty
+        for name in images:
+            results.setdefault(event, {}).setdefault(name, np.zeros((0, 5), np.float32))
+    import copy
+    return wider_evaluation(copy.deepcopy(results), gt, iou_thresh), results

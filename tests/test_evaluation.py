@@ -61,3 +61,25 @@ def test_edge_cases_and_result_packing():
     # IoU helper: +1 convention of the reference
     o = E.pairwise_overlap(np.array([[0., 0., 9., 9.]]), np.array([[0., 0., 9., 9.], [5., 5., 14., 14.], [20., 20., 30., 30.]]))
     assert np.allclose(o[0], [1.0, 25.0 / 175.0, 0.0])
+
+
+def test_test_time_preparation_and_driver():
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 255, (300, 500, 3), dtype=np.uint8)
+    chw, f = E.prepare_test_image(img, mode=0)
+    assert chw.shape == (3, 640, 640) and chw.dtype == np.float32
+    assert np.allclose(f, [640 / 500, 384 / 300, 640 / 500, 384 / 300])       # 500x300 -> 640x384
+    assert chw[:, 384:, :].max() == 0 and chw[:, :384, :].max() > 0            # zero pad below
+    chw2, f2 = E.prepare_test_image(img, mode=2)
+    assert chw2.shape == (3, 320, 512) and np.array_equal(f2, np.ones(4, np.float32))
+    assert np.array_equal(chw2[:, :300, :500], img.transpose(2, 0, 1).astype(np.float32))
+    # a detector that returns the ground truth (in network coordinates) scores AP = 1 on every subset
+    gt = {'e': {'a': dict(boxes=np.array([[50., 60., 40., 40.], [200., 100., 80., 90.]]),
+                          easy=np.array([1]), medium=np.array([1, 2]), hard=np.array([1, 2]))}}
+
+    def detect(chw, factor):
+        b = gt['e']['a']['boxes']
+        xyxy = np.concatenate([b[:, :2], b[:, :2] + b[:, 2:]], 1) * factor / factor    # rescale=True output
+        return np.concatenate([xyxy, [[0.9], [0.8]]], 1).astype(np.float32)
+    aps, results = E.evaluate_wider(detect, [('e', 'a', img)], gt, mode=0)
+    assert all(abs(a - 1.0) < 1e-12 for a in aps) and results['e']['a'].shape == (2, 5)
