@@ -16,78 +16,66 @@ NK = 5
 
 
 def parse_ann_line(line, min_size=None, test_mode=False):
-    values = [float(x) for x in line.strip().split()]
-    bbox = np.array(values[0:4], dtype=np.float32)
-    kps = np.zeros((NK, 3), dtype=np.float32)
-    ignore = False
+    """One face line -> ``dict(bbox (4,) f32, kps (5,3) f32 [x, y, weight], ignore, cat)``."""
+    v = np.array(line.split(), dtype=np.float64)
+    box = v[:4].astype(np.float32)
+    too_small = False
     if min_size is not None:
-        assert not test_mode
-        w = bbox[2] - bbox[0]
-        h = bbox[3] - bbox[1]
-        if w < min_size or h < min_size:
-            ignore = True
-    if len(values) > 4:
-        if len(values) > 5:
-            kps = np.array(values[4:19], dtype=np.float32).reshape((NK, 3))
-            for li in range(kps.shape[0]):
-                if (kps[li, :] == -1).all():
-                    kps[li][2] = 0.0          # weight 0: landmark not annotated
-                else:
-                    assert kps[li][2] >= 0
-                    kps[li][2] = 1.0
-        elif not ignore:
-            ignore = (values[4] == 1)
-    else:
-        assert test_mode
-    return dict(bbox=bbox, kps=kps, ignore=ignore, cat='FG')
+        if test_mode:
+            raise AssertionError('min_size is a training-only filter')
+        too_small = bool((box[2] - box[0]) < min_size or (box[3] - box[1]) < min_size)
+    kps = np.zeros((NK, 3), dtype=np.float32)
+    flagged = False
+    if v.size > 5:                                   # x y flag per landmark (a trailing score may follow)
+        kps = v[4:4 + 3 * NK].astype(np.float32).reshape(NK, 3)
+        missing = (kps == -1).all(axis=1)
+        if (kps[~missing, 2] < 0).any():
+            raise AssertionError('negative landmark flag')
+        kps[:, 2] = np.where(missing, 0.0, 1.0)      # the third column becomes the loss weight
+    elif v.size == 5:                                # box + ignore flag
+        flagged = v[4] == 1
+    elif not test_mode:
+        raise AssertionError('a box without landmarks or flag is only valid in test mode')
+    return dict(bbox=box, kps=kps, ignore=bool(too_small or flagged), cat='FG')
 
 
 def load_annotations(ann_file, min_size=None, test_mode=False):
-    """List of ``dict(filename, width, height, objs)`` in file order."""
-    name = None
-    bbox_map = {}
+    """List of ``dict(filename, width, height, objs)`` in file order; training images whose face list
+    is empty are dropped."""
+    images, current = [], None
     with open(ann_file, 'r') as f:
-        for line in f:
-            line = line.strip()
-            if line.startswith('#'):
-                value = line[1:].strip().split()
-                name = value[0]
-                bbox_map[name] = dict(width=int(value[1]), height=int(value[2]), objs=[])
-                continue
-            assert name is not None
-            bbox_map[name]['objs'].append(line)
-    data_infos = []
-    for name, item in bbox_map.items():
-        objs = [parse_ann_line(l, min_size, test_mode) for l in item['objs']]
-        if len(objs) == 0 and not test_mode:
-            continue
-        data_infos.append(dict(filename=name, width=item['width'], height=item['height'], objs=objs))
-    return data_infos
+        for raw in f:
+            raw = raw.strip()
+            if raw.startswith('#'):
+                path, width, height = raw[1:].split()[:3]
+                current = dict(filename=path, width=int(width), height=int(height), objs=[])
+                # a repeated header replaces the earlier entry but keeps its position (dict semantics)
+                for k, im in enumerate(images):
+                    if im['filename'] == path:
+                        images[k] = current
+                        break
+                else:
+                    images.append(current)
+            elif current is None:
+                raise AssertionError('face line before the first "# <image>" header')
+            else:
+                current['objs'].append(parse_ann_line(raw, min_size, test_mode))
+    return [im for im in images if im['objs'] or test_mode]
 
 
 def get_ann_info(data_info):
     """``bboxes (N,4) f32, labels (N,) i64, keypointss (N,5,3) f32, bboxes_ignore, labels_ignore``."""
-    bboxes, keypointss, labels, bboxes_ignore, labels_ignore = [], [], [], [], []
-    for obj in data_info['objs']:
-        if obj['ignore']:
-            bboxes_ignore.append(obj['bbox'])
-            labels_ignore.append(0)
-        else:
-            bboxes.append(obj['bbox'])
-            labels.append(0)
-            keypointss.append(obj['kps'])
-    if not bboxes:
-        bboxes, labels, keypointss = np.zeros((0, 4)), np.zeros((0,)), np.zeros((0, NK, 3))
-    else:
-        bboxes, labels, keypointss = np.array(bboxes, ndmin=2), np.array(labels), np.array(keypointss, ndmin=3)
-    if not bboxes_ignore:
-        bboxes_ignore, labels_ignore = np.zeros((0, 4)), np.zeros((0,))
-    else:
-        bboxes_ignore, labels_ignore = np.array(bboxes_ignore, ndmin=2), np.array(labels_ignore)
-    return dict(bboxes=bboxes.astype(np.float32), labels=labels.astype(np.int64),
-                keypointss=keypointss.astype(np.float32),
-                bboxes_ignore=bboxes_ignore.astype(np.float32),
-                labels_ignore=labels_ignore.astype(np.int64))
+    used = [o for o in data_info['objs'] if not o['ignore']]
+    skipped = [o for o in data_info['objs'] if o['ignore']]
+
+    def stack(objs, key, shape):
+        if not objs:
+            return np.zeros((0,) + shape, np.float32)
+        return np.stack([o[key] for o in objs]).astype(np.float32)
+
+    return dict(bboxes=stack(used, 'bbox', (4,)), labels=np.zeros(len(used), np.int64),
+                keypointss=stack(used, 'kps', (NK, 3)),
+                bboxes_ignore=stack(skipped, 'bbox', (4,)), labels_ignore=np.zeros(len(skipped), np.int64))
 
 
 class RetinaFaceSamples:

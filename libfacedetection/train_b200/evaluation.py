@@ -24,20 +24,14 @@ THRESH_NUM = 1000
 
 
 def norm_score(pred):
-    """Min-max normalise all scores of ``{event: {image: (N,5)}}`` in place (widerface.py:159-180)."""
-    max_score, min_score = -1, 2
-    for k in pred.values():
-        for v in k.values():
-            if len(v) == 0:
-                continue
-            max_score = max(np.max(v[:, -1]), max_score)
-            min_score = min(np.min(v[:, -1]), min_score)
-    diff = max_score - min_score
-    for k in pred.values():
-        for v in k.values():
-            if len(v) == 0:
-                continue
-            v[:, -1] = (v[:, -1] - min_score).astype(np.float64) / diff
+    """Min-max normalise all scores of ``{event: {image: (N,5)}}`` in place (widerface.py:159-180;
+    the bounds start from -1 / 2 like the reference's accumulators)."""
+    arrays = [v for images in pred.values() for v in images.values() if len(v)]
+    hi = max([-1] + [np.max(v[:, -1]) for v in arrays])
+    lo = min([2] + [np.min(v[:, -1]) for v in arrays])
+    span = hi - lo
+    for v in arrays:
+        v[:, -1] = (v[:, -1] - lo).astype(np.float64) / span
     return pred
 
 
