@@ -27,10 +27,14 @@ struct Smem {
 };
 
 // mode 0: TS (A in TMEM) 3xTF32; 1: SS (A in smem) 3xTF32; 2: TS single pass (hi*hi only)
-// mode 3: SS, D = A * W (NOT transposed): B is the K-major W buffer re-read as an MN-major operand
-// mode 4: SS, D[128 x 64] = [A_hi | A_lo]^T (A_hi + A_lo)  (both operands MN-major, K = the 128 rows;
-//         M = 128 stacks the hi and lo copies through the leading byte offset); rows m and m+64 add
-//         up to (A^T A)[m][n]
+// mode 3 / 4 (not in the run list): MN-major operands in the plain SWIZZLE_128B layout -- the
+//         hardware returns zeros: 32-bit MN-major operands exist only in SWIZZLE_128B_BASE32B
+// mode 5: TS, D = A * W (NOT transposed): B = W[k][n] as an MN-major SWIZZLE_128B_BASE32B operand
+//         (variants probe the LBO / SBO semantics: blocks of 32 n `lbo` apart, 4-row groups 512 B)
+// mode 6: TS, D[128 x 64] = [X_hi ; X_lo]^T (X_hi + X_lo): A = X^T staged in TMEM (lane = column of
+//         X, hi on lanes 0..63, lo on 64..127, TMEM column = row of X), B = X as MN-major BASE32B;
+//         rows m and m+64 add up to (X^T X)[m][n].  Also checks the TMA SWIZZLE_128B_ATOM_32B
+//         landing layout (32-byte chunk index XOR (row & 3)).
 __global__ void __launch_bounds__(128) tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapA32,
                                                       const float* __restrict__ W, float* out,
                                                       int mode, int* status, int variant) {
