@@ -41,3 +41,18 @@ def shard_batch(global_batch, rank, world):
         raise ValueError(f'global batch {global_batch} is not divisible by world size {world}')
     per = global_batch // world
     return rank * per, (rank + 1) * per
+
+
+def init_from_env(backend=None):
+    """``(rank, world)`` from the torchrun environment (RANK / WORLD_SIZE / MASTER_*); initialises the
+    process group when WORLD_SIZE > 1 (NCCL if CUDA is available, else gloo).  Single process: (0, 1)."""
+    import os
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = 'nccl' if torch.cuda.is_available() else 'gloo'
+        if backend == 'nccl':
+            torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
+        dist.init_process_group(backend, rank=rank, world_size=world)
+    return rank, world
