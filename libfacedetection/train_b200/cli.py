@@ -20,20 +20,28 @@ import numpy as np
 
 def sharded_batches(samples, batch_size, epoch, rank=0, world=1, seed=0):
     """Batches of this rank for ``epoch``: one shuffled order shared by all ranks (seeded by
-    ``seed + epoch`` like ``DistributedSampler.set_epoch``), strided across ranks, faces-free
-    samples skipped, incomplete last batch dropped."""
+    ``seed + epoch`` like ``DistributedSampler.set_epoch``).  Face-less samples are removed from
+    the SHARED order first and the order is cut to a multiple of ``world * batch_size`` before the
+    strided split, so every rank runs the same number of iterations (a rank with one batch more
+    would pair its all-reduces with the next epoch of the others and hang)."""
     order = np.random.RandomState(seed + epoch).permutation(len(samples))
-    order = order[:len(order) - len(order) % world][rank::world]
-    cur = [[], [], [], []]
-    for i in order:
-        s = samples[int(i)]
-        if s[1].shape[0] == 0:
-            continue
-        for c, v in zip(cur, s):
-            c.append(v)
-        if len(cur[0]) == batch_size:
-            yield tuple(cur)
-            cur = [[], [], [], []]
+    usable = np.array([samples.num_faces(int(i)) > 0 for i in order], bool) if hasattr(samples, 'num_faces') \
+        else np.array([samples[int(i)][1].shape[0] > 0 for i in order], bool)
+    order = order[usable]
+    order = order[:len(order) - len(order) % (world * batch_size)][rank::world]
+    for k in range(0, len(order), batch_size):
+        cur = [[], [], [], []]
+        for i in order[k:k + batch_size]:
+            for c, v in zip(cur, samples[int(i)]):
+                c.append(v)
+        yield tuple(cur)
+
+
+def num_batches(samples, batch_size, world=1):
+    """Iterations per epoch of every rank (independent of the rank by construction)."""
+    n = sum(1 for i in range(len(samples))
+            if (samples.num_faces(i) if hasattr(samples, 'num_faces') else samples[i][1].shape[0]) > 0)
+    return n // (world * batch_size)
 
 
 def run_training(engine, augment, samples, epochs, batch_size, start_epoch=0, start_iter=0,
@@ -76,7 +84,8 @@ def cmd_train(args):
     np.random.seed(args.seed + rank)                        # augmentation decisions (numpy global RNG)
     samples = dataset.RetinaFaceSamples(args.ann, args.img_prefix, min_size=args.min_size)
     aug = pipeline.GpuAugmenter(eng, size=args.size,
-                                crop_choice=pipeline.CROP_CHOICE_N if args.arch == 'yunet_n' else args.crop_choice)
+                                crop_choice=args.crop_choice if args.crop_choice is not None else
+                                (pipeline.CROP_CHOICE_N if args.arch == 'yunet_n' else pipeline.CROP_CHOICE_S))
     os.makedirs(args.work_dir, exist_ok=True)
 
     def save(epoch, iteration, lr):
@@ -117,7 +126,8 @@ def main(argv=None):
     t.add_argument('--epochs', type=int, default=640)
     t.add_argument('--lr', type=float, default=0.01)
     t.add_argument('--min-size', type=float, default=None)
-    t.add_argument('--crop-choice', type=float, nargs='+', default=[0.3, 0.45, 0.6, 0.8, 1.0])
+    t.add_argument('--crop-choice', type=float, nargs='+', default=None,
+                   help='RandomSquareCrop scales (default: the configs/<arch>.py list)')
     t.add_argument('--work-dir', default='work_dirs/yunet')
     t.add_argument('--save-every', type=int, default=10)
     t.add_argument('--resume', default=None)

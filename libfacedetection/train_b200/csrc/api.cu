@@ -27,6 +27,7 @@ struct yunet_ctx {
   long long launches = 0;       // kernels launched by this ctx (bench.py's gpu_launches)
   int opt_tc_forward = 1;       // use the tcgen05 unit kernel where it applies (default on)
   int opt_tc_backward = 1;      // same for the unit backward (64->64 plain units)
+  int opt_ws_forward = 1;       // warp-specialised streaming unit kernel (unit_fwd_ws.cu) where it applies
   bool profiling = false;
   std::vector<ProfEvent> prof;
   std::vector<float> prof_ms;
@@ -293,7 +294,7 @@ int yunet_forward(yunet_ctx* ctx, const float* img, const float* params, float* 
     e = cudaMemsetAsync((char*)ws + L.stats_off, 0, L.stats_bytes, s);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "forward: memset statistics");
   }
-  if (ctx->opt_tc_forward) {
+  if (ctx->opt_tc_forward || ctx->opt_ws_forward) {
     e = cudaMemsetAsync((char*)ws + L.status_off, 0, 256, s);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "forward: memset status");
   }
@@ -335,10 +336,12 @@ int yunet_forward(yunet_ctx* ctx, const float* img, const float* params, float* 
       const double hw = (double)a.H * a.W;
       double bytes = 4.0 * B * (u.cin * hw * (u.mode == LOAD_POOL ? 4.0 : 1.0) + u.cout * hw);
       if (u.mode == LOAD_UPADD) bytes += 4.0 * B * u.cin * hw / 4.0;
-      const bool tc = ctx->opt_tc_forward && unit_fwd_tc_supported(u.cin, u.cout, u.mode);
-      Scope sc(ctx, s, (tc ? "fwd_tc:" : "fwd:") + u.name, bytes);
-      e = tc ? launch_unit_fwd_tc(u.cout, u.mode, a, ctx->num_sms, v.status(), s)
-             : launch_unit_fwd(u.cin, u.cout, u.mode, a, ctx->num_sms, s);
+      const bool ws = ctx->opt_ws_forward && unit_fwd_ws_supported(u.cin, u.cout, u.mode);
+      const bool tc = !ws && ctx->opt_tc_forward && unit_fwd_tc_supported(u.cin, u.cout, u.mode);
+      Scope sc(ctx, s, (ws ? "fwd_ws:" : tc ? "fwd_tc:" : "fwd:") + u.name, bytes);
+      e = ws ? launch_unit_fwd_ws(u.cout, u.mode, a, ctx->num_sms, v.status(), s)
+          : tc ? launch_unit_fwd_tc(u.cout, u.mode, a, ctx->num_sms, v.status(), s)
+               : launch_unit_fwd(u.cin, u.cout, u.mode, a, ctx->num_sms, s);
     }
     if (e != cudaSuccess) return fail(ctx, (int)e, "forward: unit %s: %s", u.name.c_str(), cudaGetErrorString(e));
   }
@@ -549,6 +552,7 @@ int yunet_set_option(yunet_ctx* ctx, const char* name, int value) {
   if (!ctx || !name) return -1;
   if (strcmp(name, "tc_forward") == 0) { ctx->opt_tc_forward = value ? 1 : 0; return 0; }
   if (strcmp(name, "tc_backward") == 0) { ctx->opt_tc_backward = value ? 1 : 0; return 0; }
+  if (strcmp(name, "ws_forward") == 0) { ctx->opt_ws_forward = value ? 1 : 0; return 0; }
   return fail(ctx, -1, "unknown option %s", name);
 }
 

@@ -116,6 +116,11 @@ int unit_fwd_tc_supported(int cin, int cout, int mode);
 cudaError_t launch_unit_fwd_tc(int cout, int mode, const UnitFwdArgs& a, int num_sms, int* status,
                                cudaStream_t s);
 
+// ---- unit_fwd_ws.cu: warp-specialised streaming version (strips, TMA ring, TMEM double buffers) ----
+int unit_fwd_ws_supported(int cin, int cout, int mode);
+cudaError_t launch_unit_fwd_ws(int cout, int mode, const UnitFwdArgs& a, int num_sms, int* status,
+                               cudaStream_t s);
+
 // ---- unit_bwd_tc.cu: tcgen05 version of the fused unit backward (64 -> 64, plain load, BN) ----
 int unit_bwd_tc_supported(int cin, int cout, int mode, int has_bn);
 cudaError_t launch_unit_bwd_tc(int mode, const UnitBwdArgs& a, int num_sms, int* status,

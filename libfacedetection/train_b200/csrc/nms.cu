@@ -7,6 +7,7 @@
 // greedily suppress IoU > iou_thr with IoU = inter / (a + b - inter) (no +1 offset), emit
 // [x1,y1,x2,y2,score] in score order.  fp32 operation order follows the CPU kernel the reference
 // ends up in, so results are bit-comparable.
+#include <cstdint>
 #include <cstdio>
 
 #include "kernels.h"
@@ -38,14 +39,21 @@ __device__ __forceinline__ unsigned ordered_bits(float f) {
   return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 
-// per-image scratch in the caller's workspace: sorted candidate prior indices
+// GLOBAL = false: keys / boxes live in shared memory (P <= 8704: every training / 640x640 shape).
+// GLOBAL = true : the same algorithm on a per-image scratch area of the caller's workspace (keys
+// [npow2] u64, then boxes / scores / indices / flags [P]) for origin-size evaluation inputs
+// (WIDER test modes 1 / 2, tools/test_widerface.py:80-92: tens of thousands of priors per image).
+template <bool GLOBAL>
 __global__ void __launch_bounds__(NT) decode_nms_kernel(
     const LevelGeom geo, const float* __restrict__ preds, float score_thr, float iou_thr,
     const float* __restrict__ scale_factors, int max_det, float* __restrict__ dets,
-    float* __restrict__ det_kps, int* __restrict__ det_count, int npow2_cap) {
+    float* __restrict__ det_kps, int* __restrict__ det_count, int npow2_cap,
+    unsigned char* __restrict__ scratch, size_t scratch_stride) {
   extern __shared__ float4 smem_raw[];
-  // region A: sort keys (u64) [npow2]  — later reused as boxes float4[n] + scores[n] + idx[n]
-  unsigned long long* skey = reinterpret_cast<unsigned long long*>(smem_raw);
+  // region A: sort keys (u64) [npow2]  — shared memory: later reused as boxes float4[n] + scores[n] + idx[n]
+  unsigned char* region = GLOBAL ? scratch + (size_t)blockIdx.x * scratch_stride
+                                 : reinterpret_cast<unsigned char*>(smem_raw);
+  unsigned long long* skey = reinterpret_cast<unsigned long long*>(region);
   __shared__ int s_warp[NW];
   __shared__ int s_base;
   __shared__ int s_n;
@@ -111,44 +119,49 @@ __global__ void __launch_bounds__(NT) decode_nms_kernel(
   }
   // ---- phase 3: gather decoded boxes in sorted order (keys -> registers -> boxes over the keys)
   // each thread owns candidates tid, tid+NT, ...; read all keys first, then overwrite the region
-  constexpr int MAXPT = 17;   // ceil(8400 / 512)
+  constexpr int MAXPT = 17;   // ceil(8704 / 512)
   unsigned long long mykeys[MAXPT];
-#pragma unroll
-  for (int c = 0; c < MAXPT; ++c) {
-    const int i = tid + c * NT;
-    mykeys[c] = i < n ? skey[i] : 0ull;
-  }
-  __syncthreads();
-  float4* sbox = reinterpret_cast<float4*>(smem_raw);            // [n]
-  float* sscore = reinterpret_cast<float*>(sbox + n);            // [n]
-  int* sidx = reinterpret_cast<int*>(sscore + n);                // [n]
-  unsigned char* ssup = reinterpret_cast<unsigned char*>(sidx + n);  // [n]
-  {
+  if (!GLOBAL) {
 #pragma unroll
     for (int c = 0; c < MAXPT; ++c) {
       const int i = tid + c * NT;
-      if (i >= n) continue;
-      const unsigned long long key = mykeys[c];
-      const int p = (int)(key & 0xffffffffu);
-      const float* pr = pb + (long long)p * PC;
-      float px, py, s;
-      prior_of(geo, p, px, py, s);
-      const float cx = __fadd_rn(__fmul_rn(__ldg(pr + 1), s), px);
-      const float cy = __fadd_rn(__fmul_rn(__ldg(pr + 2), s), py);
-      const float w = __fmul_rn(expf(__ldg(pr + 3)), s);
-      const float h = __fmul_rn(expf(__ldg(pr + 4)), s);
-      float4 bx;
-      bx.x = __fsub_rn(cx, __fdiv_rn(w, 2.0f)); bx.y = __fsub_rn(cy, __fdiv_rn(h, 2.0f));
-      bx.z = __fadd_rn(cx, __fdiv_rn(w, 2.0f)); bx.w = __fadd_rn(cy, __fdiv_rn(h, 2.0f));
-      if (scale_factors != nullptr) {            // yunet_head.py:359-363
-        const float* sf = scale_factors + b * 4;
-        bx.x = __fdiv_rn(bx.x, __ldg(sf)); bx.y = __fdiv_rn(bx.y, __ldg(sf + 1));
-        bx.z = __fdiv_rn(bx.z, __ldg(sf + 2)); bx.w = __fdiv_rn(bx.w, __ldg(sf + 3));
-      }
-      sbox[i] = bx;
-      sscore[i] = __fmul_rn(sigmoid_ref(__ldg(pr + 0)), sigmoid_ref(__ldg(pr + 5)));
-      sidx[i] = p;
-      ssup[i] = 0;
+      mykeys[c] = i < n ? skey[i] : 0ull;
+    }
+    __syncthreads();
+  }
+  float4* sbox = reinterpret_cast<float4*>(GLOBAL ? region + (size_t)npow2_cap * 8 : region);   // [n]
+  float* sscore = reinterpret_cast<float*>(sbox + n);            // [n]
+  int* sidx = reinterpret_cast<int*>(sscore + n);                // [n]
+  unsigned char* ssup = reinterpret_cast<unsigned char*>(sidx + n);  // [n]
+  auto gather = [&](int i, unsigned long long key) {
+    const int p = (int)(key & 0xffffffffu);
+    const float* pr = pb + (long long)p * PC;
+    float px, py, s;
+    prior_of(geo, p, px, py, s);
+    const float cx = __fadd_rn(__fmul_rn(__ldg(pr + 1), s), px);
+    const float cy = __fadd_rn(__fmul_rn(__ldg(pr + 2), s), py);
+    const float w = __fmul_rn(expf(__ldg(pr + 3)), s);
+    const float h = __fmul_rn(expf(__ldg(pr + 4)), s);
+    float4 bx;
+    bx.x = __fsub_rn(cx, __fdiv_rn(w, 2.0f)); bx.y = __fsub_rn(cy, __fdiv_rn(h, 2.0f));
+    bx.z = __fadd_rn(cx, __fdiv_rn(w, 2.0f)); bx.w = __fadd_rn(cy, __fdiv_rn(h, 2.0f));
+    if (scale_factors != nullptr) {            // yunet_head.py:359-363
+      const float* sf = scale_factors + b * 4;
+      bx.x = __fdiv_rn(bx.x, __ldg(sf)); bx.y = __fdiv_rn(bx.y, __ldg(sf + 1));
+      bx.z = __fdiv_rn(bx.z, __ldg(sf + 2)); bx.w = __fdiv_rn(bx.w, __ldg(sf + 3));
+    }
+    sbox[i] = bx;
+    sscore[i] = __fmul_rn(sigmoid_ref(__ldg(pr + 0)), sigmoid_ref(__ldg(pr + 5)));
+    sidx[i] = p;
+    ssup[i] = 0;
+  };
+  if (GLOBAL) {
+    for (int i = tid; i < n; i += NT) gather(i, skey[i]);
+  } else {
+#pragma unroll
+    for (int c = 0; c < MAXPT; ++c) {
+      const int i = tid + c * NT;
+      if (i < n) gather(i, mykeys[c]);
     }
   }
   __syncthreads();
@@ -207,34 +220,49 @@ __global__ void __launch_bounds__(NT) decode_nms_kernel(
     }
     __syncthreads();
   }
-  if (tid == 0) det_count[b] = s_base;
+  // rows beyond max_det were not written: the count a caller may index with is clamped
+  if (tid == 0) det_count[b] = s_base < max_det ? s_base : max_det;
 }
 
 }  // namespace
 
+constexpr int kNmsSharedMaxP = 512 * 17;   // MAXPT bound of the shared-memory variant
+
+static size_t nms_scratch_stride(int P) {
+  int np2 = 1;
+  while (np2 < P) np2 <<= 1;
+  size_t b = (size_t)np2 * 8 + (size_t)P * (16 + 4 + 4 + 1) + 64;
+  return (b + 255) / 256 * 256;
+}
+
 size_t nms_workspace_bytes(int B, int P) {
-  (void)B; (void)P;
-  return 256;   // everything lives in shared memory; keep a non-zero size for the ABI
+  if (P <= kNmsSharedMaxP) return 256;   // everything lives in shared memory; non-zero size for the ABI
+  return (size_t)B * nms_scratch_stride(P) + 256;
 }
 
 cudaError_t launch_decode_nms(const LevelGeom& g, const float* preds, int B, float score_thr,
                               float iou_thr, const float* scale_factors, int max_det, float* dets,
                               float* det_kps, int* det_count, void* ws, cudaStream_t s) {
-  (void)ws;
-  if (g.P > 512 * 17) return cudaErrorInvalidValue;   // MAXPT bound (P <= 8704)
   int np2 = 1;
   while (np2 < g.P) np2 <<= 1;
+  if (g.P > kNmsSharedMaxP) {
+    unsigned char* scratch = reinterpret_cast<unsigned char*>(
+        (reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255));
+    decode_nms_kernel<true><<<B, NT, 0, s>>>(g, preds, score_thr, iou_thr, scale_factors, max_det, dets,
+                                             det_kps, det_count, np2, scratch, nms_scratch_stride(g.P));
+    return cudaGetLastError();
+  }
   size_t a = (size_t)np2 * sizeof(unsigned long long);
   size_t bbytes = (size_t)g.P * (16 + 4 + 4 + 1) + 64;
   size_t smem = a > bbytes ? a : bbytes;
   static size_t configured = 0;
   if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(decode_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(decode_nms_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured = smem;
   }
-  decode_nms_kernel<<<B, NT, smem, s>>>(g, preds, score_thr, iou_thr, scale_factors, max_det, dets,
-                                        det_kps, det_count, np2);
+  decode_nms_kernel<false><<<B, NT, smem, s>>>(g, preds, score_thr, iou_thr, scale_factors, max_det, dets,
+                                               det_kps, det_count, np2, nullptr, 0);
   return cudaGetLastError();
 }
 

@@ -48,6 +48,17 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
   return false;
 }
 
+// bounded wait that also leaves as soon as another role of the CTA raised the shared abort flag
+// (warp-specialised kernels: one failed wait must not leave the other roles spinning)
+__device__ __forceinline__ bool mbar_wait_abort(uint64_t* bar, uint32_t parity, volatile int* abort_flag) {
+  for (uint32_t i = 0; i < (1u << 21); ++i) {
+    if (mbar_try_wait(bar, parity)) return true;
+    if (*abort_flag != 0) return false;
+  }
+  *abort_flag = 1;
+  return false;
+}
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

@@ -126,9 +126,10 @@ template <int MODE>
 __global__ void __launch_bounds__(NT, 1)
 unit_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_du,
                    const __grid_constant__ CUtensorMap tmap_zo, const UnitBwdArgs a, int* status) {
-  extern __shared__ unsigned char smem_dyn[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>(
-      (reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) unsigned char smem_dyn[];
+  // round the base up to 1024 B with an OFFSET (not through an integer cast): the pointer stays in
+  // the shared address space for the compiler, so every access below is LDS / STS, not generic LD / ST
+  unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   unsigned char* raw = smem + Off::RAW;               // MODE 0: z_in -> a_hi; else activated a -> a_hi
   unsigned char* sAL = smem + Off::AL;               // a_lo
   unsigned char* sH = smem + Off::AL;                // MODE 1/2: h tile for the routing pass

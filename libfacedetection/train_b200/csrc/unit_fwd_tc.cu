@@ -90,9 +90,10 @@ template <int COUT, int MODE>
 __global__ void __launch_bounds__(NT, 2)
 unit_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const UnitFwdArgs a, int* status) {
   using C = TcCfg<COUT, MODE>;
-  extern __shared__ unsigned char smem_dyn[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>(
-      (reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) unsigned char smem_dyn[];
+  // round the base up to 1024 B with an OFFSET (not through an integer cast): the pointer stays in
+  // the shared address space for the compiler, so every access below is LDS / STS, not generic LD / ST
+  unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   unsigned char* raw0 = smem;                                 // NBUF x [2 m][2 kb][128 px][128 B]
   unsigned char* sBhi = smem + C::OFF_BHI;
   unsigned char* sBlo = smem + C::OFF_BLO;

@@ -100,6 +100,10 @@ class RetinaFaceSamples:
         img = self.imread(os.path.join(self.img_prefix, info['filename']))
         return img, ann['bboxes'], ann['keypointss'], ann['labels']
 
+    def num_faces(self, i):
+        """Usable (non-ignored) faces of sample ``i`` from the annotations alone (no image decode)."""
+        return int(get_ann_info(self.infos[i])['bboxes'].shape[0])
+
     def batches(self, batch_size, shuffle=True, rng=None, drop_last=True):
         """Lists ``(images, bboxes, keypointss, labels)`` of ``batch_size`` samples; images without a
         usable face (all ignored) are skipped, as RandomSquareCrop needs at least one centre."""

@@ -28,6 +28,7 @@ import torch
 from . import _capi
 
 CROP_CHOICE_N = (0.5, 0.7, 0.9, 1.1, 1.3, 1.5)       # configs/yunet_n.py:41-43
+CROP_CHOICE_S = (0.3, 0.45, 0.6, 0.8, 1.0)           # configs/yunet_s.py:41
 FLIP_ORDER = (1, 0, 2, 4, 3)
 PAD_VALUE = 128.0
 

@@ -58,15 +58,38 @@ def _leaf_rank(parts):
     return sum(order[p] for p in parts)
 
 
+def reference_state_dict_order(keys):
+    """Key order of the reference detector's ``state_dict()``: parameters in
+    ``model.parameters()`` order, every BatchNorm followed by its three buffers."""
+    keys = list(keys)
+    params = [k for k in keys if not k.endswith(('.running_mean', '.running_var', '.num_batches_tracked'))]
+    out = []
+    have = set(keys)
+    for k in reference_param_order(params):
+        out.append(k)
+        if k.endswith('.bias'):
+            prefix = k[:-len('.bias')]
+            for b in ('running_mean', 'running_var', 'num_batches_tracked'):
+                if prefix + '.' + b in have:
+                    out.append(prefix + '.' + b)
+    assert len(out) == len(keys), (len(out), len(keys))
+    return out
+
+
 def save_checkpoint(engine, path, epoch=0, iteration=0, lr=0.01, momentum=0.9, weight_decay=0.0005,
                     meta=None):
-    sd = {k: v.cpu() for k, v in engine.state_dict().items()}
+    """``state_dict`` is written in the reference's key order, so that optimizer-state index i is the
+    i-th parameter key of the file (what ``load_checkpoint`` and the reference's ``runner.resume``
+    assume); ``optimizer['param_names']`` additionally records the mapping by name."""
+    raw = {k: v.cpu() for k, v in engine.state_dict().items()}
+    sd = {k: raw[k] for k in reference_state_dict_order(raw.keys())}
     order = reference_param_order(engine)
     mom = engine.param_views(engine.momentum_buf)
     opt = {'state': {i: {'momentum_buffer': mom[n].detach().cpu().clone()} for i, n in enumerate(order)},
            'param_groups': [{'lr': lr, 'momentum': momentum, 'dampening': 0,
                              'weight_decay': weight_decay, 'nesterov': False,
-                             'params': list(range(len(order)))}]}
+                             'params': list(range(len(order)))}],
+           'param_names': list(order)}
     m = {'epoch': epoch, 'iter': iteration, 'time': time.asctime()}
     m.update(meta or {})
     torch.save({'meta': m, 'state_dict': sd, 'optimizer': opt}, path)
@@ -76,14 +99,19 @@ def load_checkpoint(engine, path, resume_optimizer=True):
     ck = torch.load(path, map_location='cpu', weights_only=False)
     engine.load_state_dict(ck['state_dict'], strict=True)
     if resume_optimizer and 'optimizer' in ck:
-        # optimizer-state indices follow model.parameters() of the code that SAVED the file, which
-        # is the key order of its state_dict (weights/yunet_s.pth lists kps before obj)
         mom = engine.param_views(engine.momentum_buf)
-        order = [k for k in ck['state_dict'] if k in mom]
+        # files written here carry the names; foreign files (the reference's own checkpoints) index
+        # the optimizer state by model.parameters() of the code that SAVED the file, which is the
+        # parameter-key order of its state_dict (weights/yunet_s.pth lists kps before obj)
+        order = ck['optimizer'].get('param_names') or [k for k in ck['state_dict'] if k in mom]
         st = ck['optimizer']['state']
         for i, n in enumerate(order):
             if i in st and 'momentum_buffer' in st[i]:
-                mom[n].copy_(st[i]['momentum_buffer'].reshape(mom[n].shape))
+                buf = st[i]['momentum_buffer']
+                if buf.numel() != mom[n].numel():
+                    raise ValueError(f'optimizer state {i} ({tuple(buf.shape)}) does not match '
+                                     f'parameter {n} {tuple(mom[n].shape)}')
+                mom[n].copy_(buf.reshape(mom[n].shape))
     return ck.get('meta', {})
 
 

@@ -54,3 +54,13 @@ def test_training_loop_schedule_and_checkpoint_cadence():
     eng2 = FakeEngine()
     it2 = cli.run_training(eng2, aug, FakeSamples(32), epochs=6, batch_size=8, start_epoch=4, start_iter=16, log_every=0)
     assert it2 == 24 and eng2.lrs == eng.lrs[16:]
+
+
+def test_every_rank_runs_the_same_number_of_batches():
+    """face-less samples are dropped from the SHARED order before the strided
+    split, so no rank gets an extra batch (which would hang the all-reduce)."""
+    for seed in range(20):
+        rng = np.random.RandomState(seed)
+        s = FakeSamples(200, empty=rng.choice(200, 9, replace=False))
+        counts = [sum(1 for _ in cli.sharded_batches(s, 4, epoch=seed, rank=r, world=2, seed=seed)) for r in range(2)]
+        assert counts[0] == counts[1] == cli.num_batches(s, 4, world=2) == (200 - 9) // 8

@@ -28,16 +28,21 @@ def _rel(a, b):
 @pytest.mark.parametrize('arch', ['yunet_n', 'yunet_s'])
 @pytest.mark.parametrize('train', [False, True])
 @pytest.mark.parametrize('shape', [(3, 96, 160), (2, 320, 320)])
-def test_tc_forward_equals_fp32_path(arch, train, shape):
+@pytest.mark.parametrize('path', ['tc', 'ws'])
+def test_tc_forward_equals_fp32_path(arch, train, shape, path):
+    """`tc`: the per-tile tcgen05 kernel (unit_fwd_tc.cu); `ws`: the warp-specialised streaming
+    kernel (unit_fwd_ws.cu).  Both against the exact-fp32 CUDA-core path."""
     B, H, W = shape
     eng = _engine(arch)
     rng = np.random.default_rng(21)
     img = torch.from_numpy(rng.random((B, 3, H, W), dtype=np.float32) * 255).cuda()
     eng.set_option('tc_forward', 0)
+    eng.set_option('ws_forward', 0)
     ref = eng.forward(img, train=train).clone()
     ref_units = [eng.read_activation(i, B, H, W, train=train).clone()
                  for i, u in enumerate(eng.ctx.units()) if u.pred_level < 0]
     eng.set_option('tc_forward', 1)
+    eng.set_option('ws_forward', 1 if path == 'ws' else 0)
     out = eng.forward(img, train=train)
     torch.cuda.synchronize()
     flags = eng.status_flags(B, H, W, train)
@@ -52,7 +57,7 @@ def test_tc_forward_equals_fp32_path(arch, train, shape):
         worst = max(worst, e)
         assert e < 1e-4, f'unit {i} {u.name.decode()}: {e:.3e}'
     e = _rel(out, ref)
-    print(f'{arch} train={train} {shape}: tc vs fp32 preds {e:.3e}, worst unit {worst:.3e}')
+    print(f'{arch} train={train} {shape} {path}: tc vs fp32 preds {e:.3e}, worst unit {worst:.3e}')
     assert e < 1e-4
 
 
@@ -60,6 +65,7 @@ def test_tc_forward_matches_reference_golden():
     g = np.load(os.path.join(GOLDEN, 'forward_yunet_n_640.npz'))
     eng = _engine('yunet_n')
     eng.set_option('tc_forward', 1)
+    eng.set_option('ws_forward', 0)
     torch.manual_seed(0)
     img = (torch.rand(1, 3, 640, 640) * 255).cuda()
     preds = eng.forward(img, train=False)
