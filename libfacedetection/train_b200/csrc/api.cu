@@ -339,7 +339,7 @@ int yunet_forward(yunet_ctx* ctx, const float* img, const float* params, float* 
       const bool ws = ctx->opt_ws_forward && unit_fwd_ws_supported(u.cin, u.cout, u.mode);
       const bool tc = !ws && ctx->opt_tc_forward && unit_fwd_tc_supported(u.cin, u.cout, u.mode);
       Scope sc(ctx, s, (ws ? "fwd_ws:" : tc ? "fwd_tc:" : "fwd:") + u.name, bytes);
-      e = ws ? launch_unit_fwd_ws(u.cout, u.mode, a, ctx->num_sms, v.status(), s)
+      e = ws ? launch_unit_fwd_ws(u.cin, u.cout, u.mode, a, ctx->num_sms, v.status(), s)
           : tc ? launch_unit_fwd_tc(u.cout, u.mode, a, ctx->num_sms, v.status(), s)
                : launch_unit_fwd(u.cin, u.cout, u.mode, a, ctx->num_sms, s);
     }

@@ -16,6 +16,21 @@ __device__ __forceinline__ void fma2(float& c0, float& c1, float a0, float a1, f
   asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(C) : "l"(A), "l"(B));
   asm("mov.b64 {%0, %1}, %2;" : "=f"(c0), "=f"(c1) : "l"(C));
 }
+// packed add / subtract (FADD2): (a0 + b0, a1 + b1), (a0 - b0, a1 - b1), IEEE round-to-nearest
+__device__ __forceinline__ void add2(float& c0, float& c1, float a0, float a1, float b0, float b1) {
+  unsigned long long A, B, C;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(A) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(B) : "f"(b0), "f"(b1));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(C) : "l"(A), "l"(B));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(c0), "=f"(c1) : "l"(C));
+}
+__device__ __forceinline__ void sub2(float& c0, float& c1, float a0, float a1, float b0, float b1) {
+  unsigned long long A, B, C;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(A) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(B) : "f"(b0), "f"(b1));
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(C) : "l"(A), "l"(B));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(c0), "=f"(c1) : "l"(C));
+}
 // acc = a * b + acc, component-wise
 __device__ __forceinline__ void fma4p(float4& acc, const float4& a, const float4& b) {
   fma2(acc.x, acc.y, a.x, a.y, b.x, b.y);

@@ -118,7 +118,7 @@ cudaError_t launch_unit_fwd_tc(int cout, int mode, const UnitFwdArgs& a, int num
 
 // ---- unit_fwd_ws.cu: warp-specialised streaming version (strips, TMA ring, TMEM double buffers) ----
 int unit_fwd_ws_supported(int cin, int cout, int mode);
-cudaError_t launch_unit_fwd_ws(int cout, int mode, const UnitFwdArgs& a, int num_sms, int* status,
+cudaError_t launch_unit_fwd_ws(int cin, int cout, int mode, const UnitFwdArgs& a, int num_sms, int* status,
                                cudaStream_t s);
 
 // ---- unit_bwd_tc.cu: tcgen05 version of the fused unit backward (64 -> 64, plain load, BN) ----

@@ -48,12 +48,30 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
   return false;
 }
 
+// try_wait with a suspend-time hint (ns): the warp sleeps in hardware until the phase completes or the
+// hint expires instead of burning issue slots in a polling loop
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
 // bounded wait that also leaves as soon as another role of the CTA raised the shared abort flag
-// (warp-specialised kernels: one failed wait must not leave the other roles spinning)
+// (warp-specialised kernels: one failed wait must not leave the other roles spinning).  A failed
+// try_wait returns after a few dozen cycles, so an un-throttled loop of waiting warps takes a third
+// of the SM's issue slots away from the working warps (measured: profiles/r2_*): back off with a
+// short nanosleep between polls.
 __device__ __forceinline__ bool mbar_wait_abort(uint64_t* bar, uint32_t parity, volatile int* abort_flag) {
-  for (uint32_t i = 0; i < (1u << 21); ++i) {
+  if (mbar_try_wait(bar, parity)) return true;
+  for (uint32_t i = 0; i < (1u << 22); ++i) {
+    __nanosleep(40);
     if (mbar_try_wait(bar, parity)) return true;
-    if (*abort_flag != 0) return false;
+    if ((i & 63u) == 63u && *abort_flag != 0) return false;
   }
   *abort_flag = 1;
   return false;
@@ -125,6 +143,18 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
           "r"(taddr),
       "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
       "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {

@@ -1,4 +1,4 @@
-// Fused ConvDPUnit forward (CIN = 64) as a warp-specialised, persistent streaming pipeline (sm_100a).
+// Fused ConvDPUnit forward as a warp-specialised, persistent streaming pipeline (sm_100a).
 // Reference semantics: mmdet/models/utils/yunet_layer.py:30-36  (relu(bn(dw3x3(pw1x1(x))))).
 //
 // The image is cut into vertical STRIPS of SW (<= 40) interior columns; a strip is streamed top to
@@ -12,19 +12,21 @@
 //
 // Roles (one CTA per SM, every role loops over the CTA's blocks; all hand-offs are mbarriers):
 //   producer  MODE 0: one thread issues the TMA boxes of block j+2 (cp.async.bulk.tensor.4d,
-//             SWIZZLE_128B, zero fill outside the image) into a 3-stage shared-memory ring.
+//             SWIZZLE_128B / 64B, zero fill outside the image) into a 3-stage shared-memory ring.
 //             MODE 1/2: four loader warps read the 2x2 max-pool window / the up-add pair with
 //             128-bit coalesced loads, apply BN+ReLU and write the same swizzled layout.
-//   convert   4 warps, thread = pixel = TMEM lane: BN + ReLU, tf32 hi/lo split (3xTF32: single
-//             TF32 misses the 1e-3 parity bar), tcgen05.st into one of two A buffers in TMEM.
-//   mma       one elected thread: 24 x tcgen05.mma.kind::tf32 (A from TMEM, W1 hi/lo K-major SW128 in
-//             shared memory), accumulators double-buffered in TMEM, tcgen05.commit -> mbarrier.
-//   epilogue  the convert warps again (convert(j+1) runs before epilogue(j), so it overlaps the MMAs
-//             of block j): tcgen05.ld, + bias, zero outside the image, -> y ring (2 slots).
-//   depthwise 5 warps (COUT = 64): thread = (4 output columns, 4 channels); per block row 6 LDS.128,
-//             3x3 stencil on the register window, z stored once with 128-bit coalesced stores,
-//             BN statistics (fp32 per block, fp64 across blocks).
+//   convert   thread = pixel = TMEM lane: BN + ReLU (FFMA2), tf32 hi/lo split (3xTF32: single
+//             TF32 misses the 1e-3 parity bar), tcgen05.st into the A buffer of the block's parity.
+//             MODE 0 runs TWO groups of 4 warps that ping-pong on even / odd blocks, so one
+//             group converts while the other waits for its MMAs and drains the accumulator.
+//   mma       one elected thread: 3 x CIN/8 tcgen05.mma.kind::tf32 (A from TMEM, W1 hi/lo K-major
+//             SW128 in shared memory), accumulators double-buffered in TMEM, tcgen05.commit.
+//   epilogue  the convert warps: tcgen05.ld, + bias (FADD2), zero outside the image -> y ring (2 slots).
+//   depthwise warp = 4 output columns, lane = channel pair; per block row 6 LDS.64, 3x3 stencil on
+//             the register window (FFMA2), z stored once (coalesced 256 B per pixel), BN statistics
+//             (fp32 per block, fp64 across blocks).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "kernels.h"
@@ -45,6 +47,7 @@ struct StripGeom {
   int NB;    // blocks per strip = ceil((H + 2) / RB)
   int nsx;   // strips per image
   int G;     // blocks in total = B * nsx * NB
+  int dbg;   // YUNET_WS_DBG bit mask (perf experiments only): 1 skip depthwise work, 2 skip convert work, 4 skip epilogue work
 };
 
 __device__ __forceinline__ void bn_coeffs_ws(const BnRef& r, int c, float& scale, float& shift) {
@@ -62,42 +65,52 @@ __device__ __forceinline__ void bn_coeffs_ws(const BnRef& r, int c, float& scale
   shift = r.beta[c] - m * scale;
 }
 
-constexpr int CIN = 64;
 constexpr int NS = 3;                        // input ring stages
 constexpr int NY = 2;                        // y ring slots
-constexpr uint32_t STAGE_BYTES = 32768;      // 2 channel blocks x 128 pixels x 128 B
 constexpr uint32_t TMEM_COLS = 512;
-constexpr uint32_t COL_A = 0;                // A buffer b: hi at b*128, lo at b*128 + 64
+constexpr uint32_t COL_A = 0;                // A buffer b: hi at b*128, lo at b*128 + CIN
 constexpr uint32_t COL_D = 256;              // D buffer b at 256 + b*64
 
-template <int COUT, int MODE>
+template <int CIN, int COUT, int MODE>
 struct WsCfg {
-  static constexpr int NQ = COUT / 4;                  // channel quads
-  static constexpr int DW_THREADS = 10 * NQ;           // 10 column groups of 4
-  static constexpr int DW_WARPS = (DW_THREADS + 31) / 32;
+  static constexpr int ROWB = (CIN >= 32 ? 32 : CIN) * 4;   // bytes of one pixel row of a k-block (128 / 64)
+  static constexpr int NKB = CIN >= 32 ? CIN / 32 : 1;      // k-blocks of 32 channels
+  static constexpr int CPR = ROWB / 16;                     // 16-byte chunks per k-block row
+  static constexpr int NCH = CIN / 4;                       // 16-byte chunks per pixel
+  static constexpr uint32_t KB_BYTES = 128 * ROWB;
+  static constexpr uint32_t STAGE_BYTES = NKB * KB_BYTES;
+  static constexpr int KS = CIN / 8;                        // k-steps (tf32: K = 8 per MMA)
+  static constexpr int NP = COUT / 2;                       // channel pairs (depthwise lanes)
+  static constexpr int CGW = 32 / NP;                       // column groups per depthwise warp
+  static constexpr int DW_WARPS = (10 + CGW - 1) / CGW;
+  static constexpr int NG = (MODE == 0) ? 2 : 1;            // convert / epilogue groups
+  static constexpr int LAG = (NG == 1) ? 1 : 0;             // NG == 1: convert(j+1) before epilogue(j)
   static constexpr int LD_WARPS = (MODE == 0) ? 0 : 4;
-  static constexpr int W_TMA = 0, W_MMA = 1, W_CV = 2, W_DW = 6;
+  static constexpr int W_TMA = 0, W_MMA = 1, W_CV = 2;
+  static constexpr int W_DW = W_CV + 4 * NG;
   static constexpr int W_LD = W_DW + DW_WARPS;
   static constexpr int NWARPS = W_LD + LD_WARPS;
   static constexpr int NT = NWARPS * 32;
-  static constexpr uint32_t YSLOT = 128 * COUT * 4;
-  static constexpr uint32_t B_BLOCK = COUT * 128;      // one k-block (32 channels) of W1 hi (or lo)
+  static constexpr int YROW = COUT * 4;                     // bytes of one y pixel
+  static constexpr uint32_t YSLOT = 128 * YROW;
+  static constexpr uint32_t B_BLOCK = COUT * 128;           // one k-block (32 channels) of W1 hi (or lo)
   static constexpr uint32_t OFF_IN = 0;
-  static constexpr uint32_t OFF_Y = OFF_IN + NS * STAGE_BYTES;
-  static constexpr uint32_t OFF_BHI = OFF_Y + ((NY * YSLOT + 1023) / 1024) * 1024;
-  static constexpr uint32_t OFF_BLO = OFF_BHI + 2 * B_BLOCK;
-  static constexpr uint32_t OFF_W2 = OFF_BLO + 2 * B_BLOCK;           // [9][COUT]
+  static constexpr uint32_t OFF_Y = (NS * STAGE_BYTES + 1023) / 1024 * 1024;
+  static constexpr uint32_t OFF_BHI = OFF_Y + (NY * YSLOT + 1023) / 1024 * 1024;
+  static constexpr uint32_t OFF_BLO = OFF_BHI + (NKB * B_BLOCK + 1023) / 1024 * 1024;
+  static constexpr uint32_t OFF_W2 = OFF_BLO + (NKB * B_BLOCK + 1023) / 1024 * 1024;   // [9][COUT]
   static constexpr uint32_t OFF_B1 = OFF_W2 + 9 * COUT * 4;
   static constexpr uint32_t OFF_B2 = OFF_B1 + COUT * 4;
-  static constexpr uint32_t OFF_SC = OFF_B2 + COUT * 4;               // [64] scale / shift of operand a
+  static constexpr uint32_t OFF_SC = OFF_B2 + COUT * 4;               // scale / shift of operand a
   static constexpr uint32_t OFF_SH = OFF_SC + CIN * 4;
   static constexpr uint32_t OFF_SCB = OFF_SH + CIN * 4;               // operand b (up-add)
   static constexpr uint32_t OFF_SHB = OFF_SCB + CIN * 4;
-  static constexpr uint32_t OFF_RED = OFF_SHB + CIN * 4;              // double [DW_WARPS][2][COUT]
-  static constexpr uint32_t OFF_BAR = OFF_RED + DW_WARPS * 2 * COUT * 8;
+  static constexpr uint32_t OFF_RED = OFF_SHB + CIN * 4;              // double [10 column groups][2][COUT]
+  static constexpr uint32_t OFF_BAR = OFF_RED + 10 * 2 * COUT * 8;
   static constexpr uint32_t SMEM = OFF_BAR + 256;
-  static_assert((2 * B_BLOCK) % 1024 == 0, "operand alignment");
   static_assert(OFF_RED % 8 == 0 && OFF_BAR % 8 == 0, "alignment");
+  static_assert(CIN == 16 || CIN == 32 || CIN == 64, "CIN");
+  static_assert(COUT == 16 || COUT == 32 || COUT == 64, "COUT");
 };
 
 // barrier indices
@@ -128,19 +141,46 @@ struct BlkIter {
   }
 };
 
+// swizzle term of a y-ring pixel: depends on the pixel's COLUMN inside the block row only, so the
+// depthwise stage can keep fixed per-thread column offsets and add a uniform row offset
+template <int COUT>
+__device__ __forceinline__ int y_swz(int col) { return COUT == 16 ? ((col >> 1) & 3) : (col & 7); }
+
+__device__ __forceinline__ float2 lds64(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+  return v;
+}
+
+// Swizzled row accesses as  (A ^ imm) + imm  computed next to the access (volatile): the compiler
+// otherwise hoists the 16 loop-invariant swizzled addresses of a row out of the block loop and
+// spills them (measured: 13 LDL per epilogue).  A = row base | (swizzle << 4), row base 16*CPR aligned.
+__device__ __forceinline__ float4 lds128_xor(uint32_t A, uint32_t x) {
+  float4 v;
+  asm volatile("{\n\t.reg .u32 t;\n\txor.b32 t, %4, %5;\n\tld.shared.v4.f32 {%0, %1, %2, %3}, [t];\n\t}"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(A), "r"(x));
+  return v;
+}
+__device__ __forceinline__ void sts128_xor(uint32_t A, uint32_t xr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("{\n\t.reg .u32 t;\n\txor.b32 t, %0, %1;\n\tst.shared.v4.b32 [t], {%2, %3, %4, %5};\n\t}" ::"r"(A),
+               "r"(xr), "r"(x), "r"(y), "r"(z), "r"(w)
+               : "memory");
+}
+
 #ifdef YUNET_WS_TIMING
 #define WT_DECL long long wt_t = clock64();
-#define WT(k) do { if (blockIdx.x == 0 && lane == 0 && COUT == 64 && MODE == 0 && a.H >= 80) { const long long t_ = clock64(); atomicAdd(status + 32 + (k), (int)(t_ - wt_t)); wt_t = t_; } } while (0)
+#define WT(k) do { if (blockIdx.x == 0 && lane == 0 && CIN == 64 && COUT == 64 && MODE == 0 && a.H >= 80) { const long long t_ = clock64(); atomicAdd(status + 32 + (k), (int)(t_ - wt_t)); wt_t = t_; } } while (0)
 #else
 #define WT_DECL
 #define WT(k)
 #endif
 
-template <int COUT, int MODE, int RBT>
-__global__ void __launch_bounds__(WsCfg<COUT, MODE>::NT, 1)
+template <int CIN, int COUT, int MODE, int RBT>
+__global__ void __launch_bounds__(WsCfg<CIN, COUT, MODE>::NT, 1)
 unit_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap, const UnitFwdArgs a, const StripGeom geo,
                    int* status) {
-  using C = WsCfg<COUT, MODE>;
+  using C = WsCfg<CIN, COUT, MODE>;
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
   // round the base up to 1024 B with an OFFSET (not through an integer cast): the pointer stays in
   // the shared address space for the compiler, so every access below is LDS / STS, not generic LD / ST
@@ -206,6 +246,7 @@ unit_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap, const UnitFwdArgs a
       sScB[tid] = sc; sShB[tid] = sh;
     }
   }
+  for (int i = tid; i < 10 * 2 * COUT; i += C::NT) sRed[i] = 0.0;
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -224,17 +265,17 @@ unit_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap, const UnitFwdArgs a
     if (MODE == 0 && lane == 0) {
       BlkIter it;
       it.init(gstart, geo);
-      const uint32_t box_bytes = (uint32_t)(RB * SWH) * 128u * 2u;
+      const uint32_t box_bytes = (uint32_t)(RB * SWH) * (uint32_t)(C::ROWB * C::NKB);
       for (int j = 0; j < nblk; ++j, it.next(geo)) {
         const int s = j % NS;
         const uint32_t par = (uint32_t)((j / NS) & 1);
         if (!mbar_wait_abort(&bars[BAR_IN_EMPTY + s], par ^ 1u, abort_flag)) { atomicExch(status, 21); break; }
         uint64_t* bar = &bars[BAR_IN_FULL + s];
-        unsigned char* dst = sIn + s * STAGE_BYTES;
+        unsigned char* dst = sIn + s * C::STAGE_BYTES;
         mbar_arrive_expect_tx(bar, box_bytes);
         const int x = it.sx * geo.SW - 1, y = it.blk * RB - 1;
-        tma_load_4d(dst, &tmap, bar, 0, x, y, it.b);
-        tma_load_4d(dst + 16384, &tmap, bar, 32, x, y, it.b);
+#pragma unroll
+        for (int kb = 0; kb < C::NKB; ++kb) tma_load_4d(dst + kb * C::KB_BYTES, &tmap, bar, kb * 32, x, y, it.b);
       }
     }
   } else if (warp == C::W_MMA) {
@@ -254,12 +295,12 @@ unit_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap, const UnitFwdArgs a
       if (ok) {
         tc_fence_after();
         const uint32_t dcol = tbase + COL_D + buf * 64;
-        const uint32_t ahi = tbase + COL_A + buf * 128, alo = ahi + 64;
+        const uint32_t ahi = tbase + COL_A + buf * 128, alo = ahi + CIN;
         uint32_t acc = 0;
 #pragma unroll
         for (int pass = 0; pass < 3; ++pass) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
+          for (int k = 0; k < C::KS; ++k) {
             const uint32_t koff = ((k >> 2) * C::B_BLOCK + (k & 3) * 32) >> 4;
             mma_tf32_ts_elect(dcol, (pass == 0 ? alo : ahi) + k * 8, (pass == 1 ? dblo : dbhi) + koff, idesc, acc);
             acc = 1;
@@ -269,18 +310,17 @@ unit_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap, const UnitFwdArgs a
       }
       WT(1);
     }
-  } else if (warp >= C::W_CV && warp < C::W_CV + 4) {
+  } else if (warp >= C::W_CV && warp < C::W_CV + 4 * C::NG) {
     // ================================================================= convert + epilogue
+    const int grp = (warp - C::W_CV) >> 2;              // ping-pong group: blocks j == grp (mod NG)
     const int quarter = warp & 3;                       // TMEM lane quarter of this warp
     const int m = quarter * 32 + lane;                  // pixel of the block == TMEM lane
     const uint32_t lane_addr = tbase + ((uint32_t)(quarter * 32) << 16);
     const int mr = m / SWH, mc = m - mr * SWH;
-    const bool mvalid = m < RB * SWH;
-    BlkIter itc, ite;
-    itc.init(gstart, geo);
-    ite = itc;
+    const int swz_in = (C::ROWB == 128) ? (m & 7) : ((m >> 1) & 3);
+    const int yx = y_swz<COUT>(mc);
     bool ok = true;
-    for (int j = 0; j <= nblk && ok; ++j) {
+    for (int j = grp; j < nblk + C::LAG * C::NG && ok; j += C::NG) {
       WT_DECL
       if (j < nblk) {
         // ---- convert block j
@@ -288,33 +328,42 @@ unit_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap, const UnitFwdArgs a
         if (!mbar_wait_abort(&bars[BAR_IN_FULL + s], (uint32_t)((j / NS) & 1), abort_flag)) { if (lane == 0) atomicExch(status, 24); ok = false; }
         ok = __all_sync(0xffffffffu, ok);
         WT(2);
-        if (ok) {
-          const unsigned char* rowp = sIn + s * STAGE_BYTES + m * 128;
+        if (ok && !(geo.dbg & 2)) {
+          const uint32_t rowA = smem_u32(sIn) + s * C::STAGE_BYTES + m * C::ROWB + (swz_in << 4);
           const uint32_t acol = lane_addr + COL_A + buf * 128;
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
+          for (int g = 0; g < CIN / 16; ++g) {
             uint32_t hi[16], lo[16];
 #pragma unroll
             for (int c4 = 0; c4 < 4; ++c4) {
               const int c = g * 4 + c4;
-              const int kb = c >> 3, cc = c & 7;
-              const float4 z = *reinterpret_cast<const float4*>(rowp + kb * 16384 + ((cc ^ (m & 7)) << 4));
+              const int kb = c / C::CPR, cc = c % C::CPR;
+              const float4 z = lds128_xor(rowA + kb * C::KB_BYTES, (uint32_t)(cc << 4));
               float v0 = z.x, v1 = z.y, v2 = z.z, v3 = z.w;     // MODE 1/2: already activated
               if (MODE == 0) {
                 const float4 sc = *reinterpret_cast<const float4*>(sSc + c * 4);
                 const float4 sh = *reinterpret_cast<const float4*>(sSh + c * 4);
-                v0 = fmaxf(fmaf(z.x, sc.x, sh.x), 0.f); v1 = fmaxf(fmaf(z.y, sc.y, sh.y), 0.f);
-                v2 = fmaxf(fmaf(z.z, sc.z, sh.z), 0.f); v3 = fmaxf(fmaf(z.w, sc.w, sh.w), 0.f);
+                v0 = sh.x; v1 = sh.y; v2 = sh.z; v3 = sh.w;
+                fma2(v0, v1, z.x, z.y, sc.x, sc.y);
+                fma2(v2, v3, z.z, z.w, sc.z, sc.w);
+                v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f);
               }
-              hi[c4 * 4 + 0] = tf32_hi(v0); lo[c4 * 4 + 0] = tf32_lo(v0);
-              hi[c4 * 4 + 1] = tf32_hi(v1); lo[c4 * 4 + 1] = tf32_lo(v1);
-              hi[c4 * 4 + 2] = tf32_hi(v2); lo[c4 * 4 + 2] = tf32_lo(v2);
-              hi[c4 * 4 + 3] = tf32_hi(v3); lo[c4 * 4 + 3] = tf32_lo(v3);
+              const float h0 = __uint_as_float(tf32_hi(v0)), h1 = __uint_as_float(tf32_hi(v1));
+              const float h2 = __uint_as_float(tf32_hi(v2)), h3 = __uint_as_float(tf32_hi(v3));
+              float l0, l1, l2, l3;
+              sub2(l0, l1, v0, v1, h0, h1);
+              sub2(l2, l3, v2, v3, h2, h3);
+              hi[c4 * 4 + 0] = __float_as_uint(h0); hi[c4 * 4 + 1] = __float_as_uint(h1);
+              hi[c4 * 4 + 2] = __float_as_uint(h2); hi[c4 * 4 + 3] = __float_as_uint(h3);
+              lo[c4 * 4 + 0] = __float_as_uint(l0); lo[c4 * 4 + 1] = __float_as_uint(l1);
+              lo[c4 * 4 + 2] = __float_as_uint(l2); lo[c4 * 4 + 3] = __float_as_uint(l3);
             }
             tmem_st16(acol + g * 16, hi);
-            tmem_st16(acol + 64 + g * 16, lo);
+            tmem_st16(acol + CIN + g * 16, lo);
           }
           tmem_wait_st();
+        }
+        if (ok) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
@@ -322,67 +371,91 @@ unit_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap, const UnitFwdArgs a
             mbar_arrive(&bars[BAR_IN_EMPTY + s]);
           }
         }
-        itc.next(geo);
         WT(3);
       }
-      if (j >= 1 && ok) {
-        // ---- epilogue of block j-1
-        const int jj = j - 1, buf = jj & 1, slot = jj % NY;
+      const int jj = j - C::LAG * C::NG;
+      if (jj >= 0 && ok) {
+        // ---- epilogue of block jj
+        const int buf = jj & 1, slot = jj % NY;
         if (!mbar_wait_abort(&bars[BAR_MMA_DONE + buf], (uint32_t)((jj >> 1) & 1), abort_flag)) { if (lane == 0) atomicExch(status, 25); ok = false; }
         ok = __all_sync(0xffffffffu, ok);
         WT(4);
         if (ok) {
           tc_fence_after();
-          uint32_t v[COUT];
-#pragma unroll
-          for (int g = 0; g < COUT / 16; ++g) tmem_ld16(lane_addr + COL_D + buf * 64 + g * 16, v + g * 16);
-          tmem_wait_ld();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bars[BAR_D_EMPTY + buf]);
+          // the accumulator row of this pixel, RAW (bias and the zero padding of y are applied by the
+          // depthwise stage, see there): tcgen05.ld -> registers -> y ring
           if (!mbar_wait_abort(&bars[BAR_Y_EMPTY + slot], (uint32_t)(((jj / NY) & 1) ^ 1), abort_flag)) { if (lane == 0) atomicExch(status, 26); ok = false; }
           ok = __all_sync(0xffffffffu, ok);
           WT(5);
           if (ok) {
-            const int gy = ite.blk * RB - 1 + mr, gx = ite.sx * geo.SW - 1 + mc;
-            const bool in = mvalid && gy >= 0 && gy < a.H && gx >= 0 && gx < a.W;
-            unsigned char* yrow = sY + slot * C::YSLOT + m * (COUT * 4);
-            const int yx = (COUT == 64) ? (m & 7) : ((m >> 1) & 3);
+            const uint32_t yA = smem_u32(sY) + slot * C::YSLOT + m * C::YROW + (yx << 4);
+            constexpr int PW = COUT < 32 ? COUT : 32;       // accumulator columns per piece (register budget)
 #pragma unroll
-            for (int c = 0; c < COUT / 4; ++c) {
-              const float4 bb = *reinterpret_cast<const float4*>(sB1 + c * 4);
-              float4 o;
-              o.x = in ? __uint_as_float(v[c * 4 + 0]) + bb.x : 0.f;
-              o.y = in ? __uint_as_float(v[c * 4 + 1]) + bb.y : 0.f;
-              o.z = in ? __uint_as_float(v[c * 4 + 2]) + bb.z : 0.f;
-              o.w = in ? __uint_as_float(v[c * 4 + 3]) + bb.w : 0.f;
-              *reinterpret_cast<float4*>(yrow + ((c ^ yx) << 4)) = o;
+            for (int h = 0; h < COUT / PW; ++h) {
+              if (geo.dbg & 4) {
+                if (h == COUT / PW - 1) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&bars[BAR_D_EMPTY + buf]); }
+                continue;
+              }
+              uint32_t v[PW];
+              if (PW == 32) tmem_ld32(lane_addr + COL_D + buf * 64 + h * 32, v);
+              else tmem_ld16(lane_addr + COL_D + buf * 64, v);
+              tmem_wait_ld();
+              if (h == COUT / PW - 1) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars[BAR_D_EMPTY + buf]);   // TMEM buffer back to the MMA warp
+              }
+#pragma unroll
+              for (int c4 = 0; c4 < PW / 4; ++c4) {
+                const int c = h * (PW / 4) + c4;
+                sts128_xor(yA, (uint32_t)(c << 4), v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
+              }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars[BAR_Y_FULL + slot]);
           }
         }
-        ite.next(geo);
         WT(6);
       }
     }
   } else if (warp >= C::W_DW && warp < C::W_DW + C::DW_WARPS) {
     // ================================================================= depthwise 3x3 + store + statistics
-    const int t = (warp - C::W_DW) * 32 + lane;
-    const int q = t % C::NQ, cg = t / C::NQ;
-    const bool active = t < C::DW_THREADS && cg * 4 < geo.SW;
-    float4 w2r[9];
+    const int q2 = lane % C::NP;                               // channel pair
+    const int cg = (warp - C::W_DW) * C::CGW + lane / C::NP;   // column group: interior columns 4cg .. 4cg+3
+    const bool active = cg < 10 && cg * 4 < geo.SW;
+    float2 w2r[9];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) w2r[k] = *reinterpret_cast<const float4*>(sW2 + k * COUT + q * 4);
-    const float4 bias2 = *reinterpret_cast<const float4*>(sB2 + q * 4);
-    float4 wa[6], wb[6];
+    for (int k = 0; k < 9; ++k) w2r[k] = *reinterpret_cast<const float2*>(sW2 + k * COUT + q2 * 2);
+    // The y ring holds the RAW pointwise result u = W1 a (no bias).  With y = u + b1 inside the image
+    // and y = 0 outside (the zero padding of the depthwise conv):
+    //   z = b2 + sum_k w2_k y_k = (b2 + b1 sum_k w2_k) + sum_k w2_k u'_k,   u' = u inside, -b1 outside,
+    // so interior blocks run on the raw values with one constant, and border blocks substitute -b1.
+    float2 bias2 = *reinterpret_cast<const float2*>(sB2 + q2 * 2);
+    const float2 b1v = *reinterpret_cast<const float2*>(sB1 + q2 * 2);
+    {
+      float sx_ = 0.f, sy_ = 0.f;
 #pragma unroll
-    for (int d = 0; d < 6; ++d) { wa[d] = make_float4(0.f, 0.f, 0.f, 0.f); wb[d] = wa[d]; }
-    double st1[4] = {0, 0, 0, 0}, st2[4] = {0, 0, 0, 0};
-    // halo columns this thread reads (clamped to the block row) and their swizzled byte offsets
-    int colp[6];
+      for (int k = 0; k < 9; ++k) { sx_ += w2r[k].x; sy_ += w2r[k].y; }
+      bias2.x = fmaf(b1v.x, sx_, bias2.x);
+      bias2.y = fmaf(b1v.y, sy_, bias2.y);
+    }
+    const float2 nb1 = make_float2(-b1v.x, -b1v.y);
+    float2 wa[6], wb[6];
 #pragma unroll
-    for (int d = 0; d < 6; ++d) { const int cc = cg * 4 + d; colp[d] = cc < SWH ? cc : SWH - 1; }
+    for (int d = 0; d < 6; ++d) { wa[d] = make_float2(0.f, 0.f); wb[d] = wa[d]; }
+    // this thread's fp64 statistics live in its private slots of the shared reduction area
+    double* myred = sRed + (cg < 10 ? cg : 0) * 2 * COUT + q2 * 2;
+    // fixed per-thread offsets of the 6 halo columns inside a block row (clamped to the row)
+    uint32_t coff[6];
+#pragma unroll
+    for (int d = 0; d < 6; ++d) {
+      int cc = cg * 4 + d;
+      if (cc > SWH - 1) cc = SWH - 1;
+      coff[d] = (uint32_t)(cc * C::YROW + (((q2 >> 1) ^ y_swz<COUT>(cc)) << 4) + (q2 & 1) * 8);
+    }
+    const uint32_t ybase = smem_u32(sY);
+    const uint32_t rowstride = (uint32_t)(SWH * C::YROW);
+    const long long grow = (long long)a.W * COUT;               // floats per output row
     BlkIter it;
     it.init(gstart, geo);
     bool ok = true;
@@ -393,77 +466,105 @@ unit_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap, const UnitFwdArgs a
       ok = __all_sync(0xffffffffu, ok);
       WT(7);
       if (!ok) break;
-      if (active) {
-        const unsigned char* ys = sY + slot * C::YSLOT;
+      if (active && !(geo.dbg & 1)) {
+        const uint32_t ys = ybase + slot * C::YSLOT;
         const bool owned = j >= prime;
         const int x0 = it.sx * geo.SW + cg * 4;
-        float* dst_img = a.zout + (long long)it.b * a.out_batch_stride + q * 4;
-        float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
-        auto row_step = [&](int ii) {
-          float4 nc[6];
+        const int orow0 = it.blk * RB - 2;
+        float* dst = a.zout + (long long)it.b * a.out_batch_stride + ((long long)orow0 * a.W + x0) * COUT + q2 * 2;
+        // fast path (interior blocks: every row and column of this thread is a real output): no
+        // predicates, no per-store address selection; the general path handles the image borders,
+        // ragged strips and the priming block
+        // (fast also needs every LOADED row / column inside the image: rows orow0+1 .. orow0+RB,
+        // columns x0-1 .. x0+4)
+        const bool fast = owned && orow0 >= 0 && orow0 + RB < a.H && (cg * 4 + 3 < geo.SW) && x0 >= 1 && (x0 + 4 < a.W);
+        float s1x = 0.f, s1y = 0.f, s2x = 0.f, s2y = 0.f;
+        if (fast) {
+          auto row_fast = [&](int ii) {
+            float2 nc[6];
+            const uint32_t rbase = ys + (uint32_t)ii * rowstride;
 #pragma unroll
-          for (int d = 0; d < 6; ++d) {
-            const int p = ii * SWH + colp[d];
-            const int sw = (COUT == 64) ? (q ^ (p & 7)) : (q ^ ((p >> 1) & 3));
-            nc[d] = *reinterpret_cast<const float4*>(ys + p * (COUT * 4) + (sw << 4));
-          }
-          const int orow = it.blk * RB + ii - 2;
-          const bool rowok = owned && orow >= 0 && orow < a.H;
+            for (int d = 0; d < 6; ++d) nc[d] = lds64(rbase + coff[d]);
+            float* drow = dst + (long long)ii * grow;
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float4 o = bias2;
+            for (int e = 0; e < 4; ++e) {
+              float ox = bias2.x, oy = bias2.y;
+              if (!(geo.dbg & 16)) {
 #pragma unroll
-            for (int d = 0; d < 3; ++d) {
-              fma4p(o, w2r[d], wa[e + d]); fma4p(o, w2r[3 + d], wb[e + d]); fma4p(o, w2r[6 + d], nc[e + d]);
+              for (int d = 0; d < 3; ++d) {
+                fma2(ox, oy, w2r[d].x, w2r[d].y, wa[e + d].x, wa[e + d].y);
+                fma2(ox, oy, w2r[3 + d].x, w2r[3 + d].y, wb[e + d].x, wb[e + d].y);
+                fma2(ox, oy, w2r[6 + d].x, w2r[6 + d].y, nc[e + d].x, nc[e + d].y);
+              }
+              } else { ox += nc[e].x + nc[e + 1].x + nc[e + 2].x; oy += nc[e].y + nc[e+1].y + nc[e+2].y; }
+              if (!(geo.dbg & 8)) *reinterpret_cast<float2*>(drow + e * COUT) = make_float2(ox, oy);
+              add2(s1x, s1y, s1x, s1y, ox, oy);
+              fma2(s2x, s2y, ox, oy, ox, oy);
             }
-            const int x = x0 + e;
-            if (rowok && cg * 4 + e < geo.SW && x < a.W) {
-              *reinterpret_cast<float4*>(dst_img + ((long long)orow * a.W + x) * COUT) = o;
-              s1.x += o.x; s1.y += o.y; s1.z += o.z; s1.w += o.w;
-              fma4p(s2, o, o);
-            }
+#pragma unroll
+            for (int d = 0; d < 6; ++d) { wa[d] = wb[d]; wb[d] = nc[d]; }
+          };
+          if (RBT > 0) {
+#pragma unroll
+            for (int ii = 0; ii < (RBT > 0 ? RBT : 1); ++ii) row_fast(ii);
+          } else {
+            for (int ii = 0; ii < RB; ++ii) row_fast(ii);
           }
-#pragma unroll
-          for (int d = 0; d < 6; ++d) { wa[d] = wb[d]; wb[d] = nc[d]; }
-        };
-        if (RBT > 0) {
-#pragma unroll
-          for (int ii = 0; ii < (RBT > 0 ? RBT : 1); ++ii) row_step(ii);
         } else {
-          for (int ii = 0; ii < RB; ++ii) row_step(ii);
+          bool cok[4], cin[6];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) cok[e] = owned && (cg * 4 + e < geo.SW) && (x0 + e < a.W);
+#pragma unroll
+          for (int d = 0; d < 6; ++d) cin[d] = (x0 - 1 + d >= 0) && (x0 - 1 + d < a.W);
+          for (int ii = 0; ii < RB; ++ii) {
+            float2 nc[6];
+            const uint32_t rbase = ys + (uint32_t)ii * rowstride;
+            const int lrow = orow0 + 1 + ii;                 // image row of the loaded y row
+            const bool rin = lrow >= 0 && lrow < a.H;
+#pragma unroll
+            for (int d = 0; d < 6; ++d) {
+              const float2 t = lds64(rbase + coff[d]);
+              nc[d] = (rin && cin[d]) ? t : nb1;
+            }
+            const int orow = orow0 + ii;
+            const bool rowok = orow >= 0 && orow < a.H;
+            float* drow = dst + (long long)ii * grow;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float ox = bias2.x, oy = bias2.y;
+#pragma unroll
+              for (int d = 0; d < 3; ++d) {
+                fma2(ox, oy, w2r[d].x, w2r[d].y, wa[e + d].x, wa[e + d].y);
+                fma2(ox, oy, w2r[3 + d].x, w2r[3 + d].y, wb[e + d].x, wb[e + d].y);
+                fma2(ox, oy, w2r[6 + d].x, w2r[6 + d].y, nc[e + d].x, nc[e + d].y);
+              }
+              if (rowok && cok[e]) {
+                *reinterpret_cast<float2*>(drow + e * COUT) = make_float2(ox, oy);
+                add2(s1x, s1y, s1x, s1y, ox, oy);
+                fma2(s2x, s2y, ox, oy, ox, oy);
+              }
+            }
+#pragma unroll
+            for (int d = 0; d < 6; ++d) { wa[d] = wb[d]; wb[d] = nc[d]; }
+          }
         }
-        st1[0] += s1.x; st1[1] += s1.y; st1[2] += s1.z; st1[3] += s1.w;
-        st2[0] += s2.x; st2[1] += s2.y; st2[2] += s2.z; st2[3] += s2.w;
+        if (a.osum != nullptr && owned) {
+          double2 t1 = *reinterpret_cast<double2*>(myred), t2 = *reinterpret_cast<double2*>(myred + COUT);
+          t1.x += s1x; t1.y += s1y; t2.x += s2x; t2.y += s2y;
+          *reinterpret_cast<double2*>(myred) = t1;
+          *reinterpret_cast<double2*>(myred + COUT) = t2;
+        }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[BAR_Y_EMPTY + slot]);
       WT(8);
     }
-    // statistics: lanes sharing a channel quad reduce in the warp, one row per warp in shared memory
-    if (a.osum != nullptr) {
-      if (!(t < C::DW_THREADS)) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) { st1[c] = 0.0; st2[c] = 0.0; }
-      }
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-#pragma unroll
-        for (int o = 16; o >= C::NQ; o >>= 1) {
-          st1[c] += __shfl_xor_sync(0xffffffffu, st1[c], o);
-          st2[c] += __shfl_xor_sync(0xffffffffu, st2[c], o);
-        }
-      }
-      if (lane < C::NQ) {
-        double* r = sRed + (warp - C::W_DW) * 2 * COUT;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) { r[lane * 4 + c] = st1[c]; r[COUT + lane * 4 + c] = st2[c]; }
-      }
-    }
   } else if (MODE != 0 && warp >= C::W_LD) {
     // ================================================================= loader warps (pool / up-add)
+    constexpr int PPI = 128 / C::NCH;                     // pixels per pass of the 128 loader threads
     const int lt = (warp - C::W_LD) * 32 + lane;          // 0..127
-    const int ch = lt & 15;                               // 16-byte chunk of the pixel row
-    const int p0 = lt >> 4;                               // first pixel; then += 8
+    const int ch = lt % C::NCH;                           // 16-byte chunk of the pixel row
+    const int p0 = lt / C::NCH;                           // first pixel; then += PPI
     const float4 sc = *reinterpret_cast<const float4*>(sSc + ch * 4);
     const float4 sh = *reinterpret_cast<const float4*>(sSh + ch * 4);
     float4 scb = sc, shb = sh;
@@ -472,6 +573,7 @@ unit_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap, const UnitFwdArgs a
       shb = *reinterpret_cast<const float4*>(sShB + ch * 4);
     }
     const int npx = RB * SWH;
+    const int kbo = (ch / C::CPR) * C::KB_BYTES, cc = ch % C::CPR;
     BlkIter it;
     it.init(gstart, geo);
     bool ok = true;
@@ -480,41 +582,61 @@ unit_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap, const UnitFwdArgs a
       if (!mbar_wait_abort(&bars[BAR_IN_EMPTY + s], (uint32_t)(((j / NS) & 1) ^ 1), abort_flag)) { if (lane == 0) atomicExch(status, 28); ok = false; }
       ok = __all_sync(0xffffffffu, ok);
       if (!ok) break;
-      unsigned char* dst = sIn + s * STAGE_BYTES + (ch >> 3) * 16384;
+      unsigned char* dst = sIn + s * C::STAGE_BYTES + kbo;
       const int gy0 = it.blk * RB - 1, gx0 = it.sx * geo.SW - 1;
-      // (row, col) of pixel p0, advanced by 8 pixels per step without divisions
+      // two pixels per step: all global loads of both first (memory-level parallelism), then the math
       int pr = p0 / SWH, pc = p0 - pr * SWH;
-#pragma unroll 4
-      for (int p = p0; p < npx; p += 8) {
-        const int gy = gy0 + pr, gx = gx0 + pc;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) {
-          if (MODE == 1) {
-            const int W2 = a.W * 2;
-            const float* src = a.za + (((long long)it.b * (a.H * 2) + gy * 2) * W2 + gx * 2) * CIN + ch * 4;
-            const float4 z00 = __ldg(reinterpret_cast<const float4*>(src));
-            const float4 z01 = __ldg(reinterpret_cast<const float4*>(src + CIN));
-            const float4 z10 = __ldg(reinterpret_cast<const float4*>(src + (long long)W2 * CIN));
-            const float4 z11 = __ldg(reinterpret_cast<const float4*>(src + (long long)W2 * CIN + CIN));
-            v.x = fmaxf(fmaxf(fmaxf(fmaf(z00.x, sc.x, sh.x), fmaf(z01.x, sc.x, sh.x)), fmaxf(fmaf(z10.x, sc.x, sh.x), fmaf(z11.x, sc.x, sh.x))), 0.f);
-            v.y = fmaxf(fmaxf(fmaxf(fmaf(z00.y, sc.y, sh.y), fmaf(z01.y, sc.y, sh.y)), fmaxf(fmaf(z10.y, sc.y, sh.y), fmaf(z11.y, sc.y, sh.y))), 0.f);
-            v.z = fmaxf(fmaxf(fmaxf(fmaf(z00.z, sc.z, sh.z), fmaf(z01.z, sc.z, sh.z)), fmaxf(fmaf(z10.z, sc.z, sh.z), fmaf(z11.z, sc.z, sh.z))), 0.f);
-            v.w = fmaxf(fmaxf(fmaxf(fmaf(z00.w, sc.w, sh.w), fmaf(z01.w, sc.w, sh.w)), fmaxf(fmaf(z10.w, sc.w, sh.w), fmaf(z11.w, sc.w, sh.w))), 0.f);
-          } else {
-            const float4 z = __ldg(reinterpret_cast<const float4*>(
-                a.za + (((long long)it.b * a.H + gy) * a.W + gx) * CIN + ch * 4));
-            const int Hb = a.H >> 1, Wb = a.W >> 1;
-            const float4 zb = __ldg(reinterpret_cast<const float4*>(
-                a.zb + (((long long)it.b * Hb + (gy >> 1)) * Wb + (gx >> 1)) * CIN + ch * 4));
-            v.x = fmaxf(fmaf(z.x, sc.x, sh.x), 0.f) + fmaxf(fmaf(zb.x, scb.x, shb.x), 0.f);
-            v.y = fmaxf(fmaf(z.y, sc.y, sh.y), 0.f) + fmaxf(fmaf(zb.y, scb.y, shb.y), 0.f);
-            v.z = fmaxf(fmaf(z.z, sc.z, sh.z), 0.f) + fmaxf(fmaf(zb.z, scb.z, shb.z), 0.f);
-            v.w = fmaxf(fmaf(z.w, sc.w, sh.w), 0.f) + fmaxf(fmaf(zb.w, scb.w, shb.w), 0.f);
+      for (int p = p0; p < npx; p += 2 * PPI) {
+        float4 zz[2][4];
+        bool inb[2];
+        int pp[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          pp[u] = p + u * PPI;
+          const int gy = gy0 + pr, gx = gx0 + pc;
+          inb[u] = pp[u] < npx && gy >= 0 && gy < a.H && gx >= 0 && gx < a.W;
+          if (inb[u]) {
+            if (MODE == 1) {
+              const int W2 = a.W * 2;
+              const float* src = a.za + (((long long)it.b * (a.H * 2) + gy * 2) * W2 + gx * 2) * CIN + ch * 4;
+              zz[u][0] = __ldg(reinterpret_cast<const float4*>(src));
+              zz[u][1] = __ldg(reinterpret_cast<const float4*>(src + CIN));
+              zz[u][2] = __ldg(reinterpret_cast<const float4*>(src + (long long)W2 * CIN));
+              zz[u][3] = __ldg(reinterpret_cast<const float4*>(src + (long long)W2 * CIN + CIN));
+            } else {
+              zz[u][0] = __ldg(reinterpret_cast<const float4*>(
+                  a.za + (((long long)it.b * a.H + gy) * a.W + gx) * CIN + ch * 4));
+              const int Hb = a.H >> 1, Wb = a.W >> 1;
+              zz[u][1] = __ldg(reinterpret_cast<const float4*>(
+                  a.zb + (((long long)it.b * Hb + (gy >> 1)) * Wb + (gx >> 1)) * CIN + ch * 4));
+            }
           }
+          pc += PPI;
+          while (pc >= SWH) { pc -= SWH; ++pr; }
         }
-        *reinterpret_cast<float4*>(dst + p * 128 + (((ch & 7) ^ (p & 7)) << 4)) = v;
-        pc += 8;
-        while (pc >= SWH) { pc -= SWH; ++pr; }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          if (pp[u] >= npx) continue;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (inb[u]) {
+            if (MODE == 1) {
+              const float4 z00 = zz[u][0], z01 = zz[u][1], z10 = zz[u][2], z11 = zz[u][3];
+              v.x = fmaxf(fmaxf(fmaxf(fmaf(z00.x, sc.x, sh.x), fmaf(z01.x, sc.x, sh.x)), fmaxf(fmaf(z10.x, sc.x, sh.x), fmaf(z11.x, sc.x, sh.x))), 0.f);
+              v.y = fmaxf(fmaxf(fmaxf(fmaf(z00.y, sc.y, sh.y), fmaf(z01.y, sc.y, sh.y)), fmaxf(fmaf(z10.y, sc.y, sh.y), fmaf(z11.y, sc.y, sh.y))), 0.f);
+              v.z = fmaxf(fmaxf(fmaxf(fmaf(z00.z, sc.z, sh.z), fmaf(z01.z, sc.z, sh.z)), fmaxf(fmaf(z10.z, sc.z, sh.z), fmaf(z11.z, sc.z, sh.z))), 0.f);
+              v.w = fmaxf(fmaxf(fmaxf(fmaf(z00.w, sc.w, sh.w), fmaf(z01.w, sc.w, sh.w)), fmaxf(fmaf(z10.w, sc.w, sh.w), fmaf(z11.w, sc.w, sh.w))), 0.f);
+            } else {
+              const float4 z = zz[u][0], zb = zz[u][1];
+              v.x = fmaxf(fmaf(z.x, sc.x, sh.x), 0.f) + fmaxf(fmaf(zb.x, scb.x, shb.x), 0.f);
+              v.y = fmaxf(fmaf(z.y, sc.y, sh.y), 0.f) + fmaxf(fmaf(zb.y, scb.y, shb.y), 0.f);
+              v.z = fmaxf(fmaf(z.z, sc.z, sh.z), 0.f) + fmaxf(fmaf(zb.z, scb.z, shb.z), 0.f);
+              v.w = fmaxf(fmaf(z.w, sc.w, sh.w), 0.f) + fmaxf(fmaf(zb.w, scb.w, shb.w), 0.f);
+            }
+          }
+          const int px = pp[u];
+          const int sw = (C::ROWB == 128) ? (px & 7) : ((px >> 1) & 3);
+          *reinterpret_cast<float4*>(dst + px * C::ROWB + ((cc ^ sw) << 4)) = v;
+        }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[BAR_IN_FULL + s]);
@@ -527,7 +649,7 @@ unit_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap, const UnitFwdArgs a
   if (a.osum != nullptr && tid < 2 * COUT) {
     double s = 0.0;
 #pragma unroll
-    for (int w = 0; w < C::DW_WARPS; ++w) s += sRed[w * 2 * COUT + tid];
+    for (int w = 0; w < 10; ++w) s += sRed[w * 2 * COUT + tid];
     if (tid < COUT) atomicAdd(a.osum + tid, s);
     else atomicAdd(a.osumsq + (tid - COUT), s);
   }
@@ -537,12 +659,12 @@ unit_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap, const UnitFwdArgs a
   }
 }
 
-template <int COUT, int MODE, int RBT>
+template <int CIN, int COUT, int MODE, int RBT>
 cudaError_t launch_ws_t(const CUtensorMap& tm, const UnitFwdArgs& a, const StripGeom& geo, int num_sms,
                         int* status, cudaStream_t s) {
-  using C = WsCfg<COUT, MODE>;
+  using C = WsCfg<CIN, COUT, MODE>;
   const size_t smem = C::SMEM + 1024;
-  auto kern = unit_fwd_ws_kernel<COUT, MODE, RBT>;
+  auto kern = unit_fwd_ws_kernel<CIN, COUT, MODE, RBT>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -555,26 +677,27 @@ cudaError_t launch_ws_t(const CUtensorMap& tm, const UnitFwdArgs& a, const Strip
   return cudaGetLastError();
 }
 
-template <int COUT, int MODE>
+template <int CIN, int COUT, int MODE>
 cudaError_t launch_ws_rb(const CUtensorMap& tm, const UnitFwdArgs& a, const StripGeom& geo, int num_sms,
                          int* status, cudaStream_t s) {
   switch (geo.RB) {
-    case 3: return launch_ws_t<COUT, MODE, 3>(tm, a, geo, num_sms, status, s);
-    case 5: return launch_ws_t<COUT, MODE, 5>(tm, a, geo, num_sms, status, s);
-    default: return launch_ws_t<COUT, MODE, 0>(tm, a, geo, num_sms, status, s);
+    case 3: return launch_ws_t<CIN, COUT, MODE, 3>(tm, a, geo, num_sms, status, s);
+    case 5: return launch_ws_t<CIN, COUT, MODE, 5>(tm, a, geo, num_sms, status, s);
+    default: return launch_ws_t<CIN, COUT, MODE, 0>(tm, a, geo, num_sms, status, s);
   }
 }
 
 }  // namespace
 
 int unit_fwd_ws_supported(int cin, int cout, int mode) {
-  if (cin != 64 || tma_encode_fn() == nullptr) return 0;
-  if (cout == 64) return mode >= 0 && mode <= 2;
-  return cout == 16 && mode == 0;
+  if (tma_encode_fn() == nullptr) return 0;
+  if (cin == 64 && cout == 64) return mode >= 0 && mode <= 2;
+  if (cin == 64 && cout == 16) return mode == 0;
+  return 0;
 }
 
 // `status`: device int, set non-zero if a bounded wait inside the kernel timed out.
-cudaError_t launch_unit_fwd_ws(int cout, int mode, const UnitFwdArgs& a, int num_sms, int* status,
+cudaError_t launch_unit_fwd_ws(int cin, int cout, int mode, const UnitFwdArgs& a, int num_sms, int* status,
                                cudaStream_t s) {
   StripGeom geo;
   geo.nsx = (a.W + 39) / 40;
@@ -584,17 +707,23 @@ cudaError_t launch_unit_fwd_ws(int cout, int mode, const UnitFwdArgs& a, int num
   if (geo.RB > a.H + 2) geo.RB = a.H + 2;
   geo.NB = (a.H + 2 + geo.RB - 1) / geo.RB;
   geo.G = a.B * geo.nsx * geo.NB;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("YUNET_WS_DBG"); dbg = e ? atoi(e) : 0; }
+    geo.dbg = dbg;
+  }
   CUtensorMap tm;
   memset(&tm, 0, sizeof tm);
   if (mode == 0) {
-    cudaError_t e = make_nhwc_map(&tm, a.za, CIN, a.W, a.H, a.B, CIN, (long long)a.H * a.W * CIN, 32,
-                                  geo.SWH, geo.RB, CU_TENSOR_MAP_SWIZZLE_128B);
+    cudaError_t e = make_nhwc_map(&tm, a.za, cin, a.W, a.H, a.B, cin, (long long)a.H * a.W * cin,
+                                  cin >= 32 ? 32 : cin, geo.SWH, geo.RB,
+                                  cin >= 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
     if (e != cudaSuccess) return e;
   }
-  if (cout == 64 && mode == 0) return launch_ws_rb<64, 0>(tm, a, geo, num_sms, status, s);
-  if (cout == 64 && mode == 1) return launch_ws_rb<64, 1>(tm, a, geo, num_sms, status, s);
-  if (cout == 64 && mode == 2) return launch_ws_rb<64, 2>(tm, a, geo, num_sms, status, s);
-  if (cout == 16 && mode == 0) return launch_ws_rb<16, 0>(tm, a, geo, num_sms, status, s);
+  if (cin == 64 && cout == 64 && mode == 0) return launch_ws_rb<64, 64, 0>(tm, a, geo, num_sms, status, s);
+  if (cin == 64 && cout == 64 && mode == 1) return launch_ws_rb<64, 64, 1>(tm, a, geo, num_sms, status, s);
+  if (cin == 64 && cout == 64 && mode == 2) return launch_ws_rb<64, 64, 2>(tm, a, geo, num_sms, status, s);
+  if (cin == 64 && cout == 16 && mode == 0) return launch_ws_rb<64, 16, 0>(tm, a, geo, num_sms, status, s);
   return cudaErrorInvalidValue;
 }
 

@@ -21,10 +21,10 @@ off = _capi.lib.yunet_ws_offset(eng.h, B, S, S, 1, 0, 3)
 ws = eng.workspace(B, S, S, True)
 st = ws[off:off + 256].view(torch.int32)
 c = st.cpu().tolist()
-names = {0: 'mma: wait a_full/d_empty (1 warp)', 1: 'mma: issue', 2: 'cv: wait in_full (4 warps)',
+names = {0: 'mma: wait a_full/d_empty (1 warp)', 1: 'mma: issue', 2: 'cv: wait in_full (2 x 4 warps, each every other block)',
          3: 'cv: convert', 4: 'ep: wait mma_done', 5: 'ep: tmem ld + wait y_empty', 6: 'ep: y store',
-         7: 'dw: wait y_full (5 warps)', 8: 'dw: stencil + store'}
-div = {0: 1, 1: 1, 2: 4, 3: 4, 4: 4, 5: 4, 6: 4, 7: 5, 8: 5}
+         7: 'dw: wait y_full (10 warps)', 8: 'dw: stencil + store', 9: 'ep: tcgen05.ld (of the y store time)'}
+div = {0: 1, 1: 1, 2: 8, 3: 8, 4: 8, 5: 8, 6: 8, 7: 10, 8: 10, 9: 8}   # warps adding to each counter
 nblk = 2 * 98   # two launches (model2.conv1/conv2), ~97 + 1 blocks each for CTA 0
 print('flags', c[:4])
 for k, n in names.items():
