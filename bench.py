@@ -46,10 +46,25 @@ def parse():
     ap.add_argument('--cpu-sample', type=int, default=32, help='images per CPU-baseline step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--kernel-table', default='', help='write the per-kernel profile here (json)')
+    ap.add_argument('--no-graph', action='store_true',
+                    help='launch every kernel of the step individually instead of replaying the captured CUDA graph')
+    ap.add_argument('--no-extra', action='store_true',
+                    help='skip the extra_configs (yunet_s train, 640x640 inference) and e2e_plugin legs')
     ap.add_argument('--workload', default='train', choices=['train', 'infer'],
                     help="'train' (default, the headline metric) or 'infer': BASELINE.json "
                          "configs[3], eval forward + decode + NMS at 640x640, bs=512")
     return ap.parse_args()
+
+
+def load_synthetic():
+    """``libfacedetection/train_b200/synthetic.py`` loaded from its file, NOT through the package:
+    importing the package dlopens libyunet_b200.so, which the CPU reference arm must not do."""
+    import importlib.util
+    path = os.path.join(ROOT, 'libfacedetection', 'train_b200', 'synthetic.py')
+    spec = importlib.util.spec_from_file_location('_yunet_synthetic_standalone', path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
 
 
 def measured_peaks():
@@ -65,7 +80,7 @@ def cpu_reference_steps(arch, sample, size, steps, warmup, seed=0):
     """The reference's own training step (CPU restatement of the unmodified Python path, all host
     threads): zero_grad -> forward_train -> _parse_losses -> backward -> SGD.step."""
     from oracle import yunet_oracle as orc
-    from libfacedetection.train_b200 import synthetic
+    synthetic = load_synthetic()
     cores = os.cpu_count() or 1
     P, Bf = orc.init_params(arch, seed=0)
     img = torch.from_numpy(synthetic.make_images(sample, size, seed))
@@ -97,7 +112,230 @@ def cpu_reference_steps(arch, sample, size, steps, warmup, seed=0):
                 sample=sample)
 
 
+def cpu_reference_infer(arch, sample, size, steps, warmup):
+    """the reference's ``simple_test`` (eval forward + get_bboxes: decode,
+    score filter, NMS) on the host cores, ``sample`` images of ``size`` x ``size`` per step."""
+    from oracle import yunet_oracle as orc
+    d = np.load(os.path.join(ROOT, 'tests', 'golden', f'weights_{arch}.npz'))
+    P, Bf = orc.split_state_dict({k: torch.from_numpy(d[k]) for k in d.files})
+    g = torch.Generator().manual_seed(0)
+    img = torch.rand(sample, 3, size, size, generator=g) * 255
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(min(cores, 32))
+
+    def one():
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            outs = orc.model_forward(img, P, Bf, arch, training=False)
+            orc.get_bboxes(*outs)
+        return time.perf_counter() - t0
+
+    for _ in range(warmup):
+        one()
+    ms = 1e3 * float(np.mean([one() for _ in range(steps)]))
+    return dict(value=sample / (ms / 1e3), ms_per_step=ms, cores=cores, threads=min(cores, 32), sample=sample)
+
+
+def step_table(eng, step_fn, reps=3):
+    """Per-launch CUDA-event profile of ``reps`` calls of ``step_fn`` -> (rows, total ms, bytes)."""
+    import ctypes as C
+    from libfacedetection.train_b200._capi import lib
+    lib.yunet_profile_begin(eng.h)
+    for _ in range(reps):
+        step_fn()
+    torch.cuda.synchronize()
+    n = lib.yunet_profile_end(eng.h)
+    name, ms, by = C.create_string_buffer(160), C.c_float(), C.c_double()
+    kern = {}
+    for i in range(n):
+        lib.yunet_profile_get(eng.h, i, name, 160, C.byref(ms), C.byref(by))
+        k = kern.setdefault(name.value.decode(), [0.0, 0.0, 0])
+        k[0] += ms.value
+        k[1] = by.value
+        k[2] += 1
+    rows = [{'kernel': k, 'ms': v[0] / v[2], 'algorithmic_bytes': v[1],
+             'gbs': (v[1] / 1e9) / (v[0] / v[2] / 1e3) if v[1] > 0 and v[0] > 0 else None}
+            for k, v in kern.items()]
+    rows.sort(key=lambda r: -r['ms'])
+    return rows
+
+
+def extra_train_config(arch, B, S, dev, peak):
+    """BASELINE.json configs[4] (yunet_s train) measured in the same process: device-resident step."""
+    from libfacedetection.train_b200 import YuNetEngine, synthetic
+    eng = YuNetEngine(arch, device=dev)
+    eng.init_weights(0)
+    img = torch.from_numpy(synthetic.make_images(B, S, 0)).to(dev)
+    gb, gl, gk = synthetic.make_gt(B, S, 0)
+    gt, offs = synthetic.pack_gt_csr(gb, gk)
+    gt, offs = torch.from_numpy(gt).to(dev), torch.from_numpy(offs).to(dev)
+    for _ in range(3):
+        eng.train_step(img, gt, offs, lr=LR)
+    torch.cuda.synchronize()
+    K = 8
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        eng.train_step(img, gt, offs, lr=LR)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / K
+    rows = step_table(eng, lambda: eng.train_step(img, gt, offs, lr=LR))
+    streaming = [r for r in rows if r['gbs'] is not None]
+    fwd = [r for r in streaming if r['kernel'].startswith('fwd')]
+    dom = streaming[0]
+    gb_all = sum(r['algorithmic_bytes'] for r in streaming) / 1e9
+    out = {'config': f'{arch} {S}x{S} train step bs={B} (BASELINE.json configs[4])',
+           'metric': METRIC, 'value': B / (ms / 1e3), 'unit': UNIT, 'ms_per_step': ms, 'steps': K,
+           'roofline': {'kernel': dom['kernel'], 'achieved': dom['gbs'], 'frac': dom['gbs'] / peak,
+                        'ms_per_launch': dom['ms'],
+                        'forward_total_frac': (sum(r['algorithmic_bytes'] for r in fwd) / 1e9) /
+                        (sum(r['ms'] for r in fwd) / 1e3) / peak,
+                        'step_total_frac': gb_all / (sum(r['ms'] for r in streaming) / 1e3) / peak}}
+    del eng
+    torch.cuda.empty_cache()
+    return out
+
+
+def extra_infer_config(arch, B, S, dev, peak, cpu=True):
+    """BASELINE.json configs[3]: eval forward + decode + NMS at 640x640, bs=512, with its own CPU
+    baseline (oracle ``simple_test`` at bs=8) and an end-to-end number from pinned host images."""
+    from libfacedetection.train_b200 import YuNetEngine
+    eng = YuNetEngine(arch, device=dev)
+    d = np.load(os.path.join(ROOT, 'tests', 'golden', f'weights_{arch}.npz'))
+    eng.load_state_dict({k: torch.from_numpy(d[k]) for k in d.files})
+    g = torch.Generator(device=dev).manual_seed(0)
+    img = torch.rand(B, 3, S, S, device=dev, generator=g) * 255
+    for _ in range(3):
+        eng.detect(img)
+    torch.cuda.synchronize()
+    K = 5
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        dets, counts, _ = eng.detect(img)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / K
+    rows = step_table(eng, lambda: eng.detect(img), reps=2)
+    streaming = [r for r in rows if r['gbs'] is not None]
+    nms_ms = sum(r['ms'] for r in rows if 'nms' in r['kernel'])
+    # end to end: images from pinned host memory, detections + counts back to the host
+    himg = torch.empty(B, 3, S, S, dtype=torch.float32).pin_memory()
+    himg.copy_(img)
+    P_ = dets.shape[1]
+    hdets = torch.empty(B, P_, 5).pin_memory()
+    hcnt = torch.empty(B, dtype=torch.int32).pin_memory()
+
+    def e2e_step():
+        img.copy_(himg, non_blocking=True)
+        dd, cc, _ = eng.detect(img)
+        hdets.copy_(dd, non_blocking=True)
+        hcnt.copy_(cc, non_blocking=True)
+
+    e2e_step()
+    torch.cuda.synchronize()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(3):
+        e2e_step()
+    s1.record()
+    torch.cuda.synchronize()
+    ms_e2e = s0.elapsed_time(s1) / 3
+    alg = sum(r['algorithmic_bytes'] for r in streaming)
+    out = {'config': f'{arch} {S}x{S} eval forward + decode + NMS, bs={B} (BASELINE.json configs[3])',
+           'metric': 'infer_images_per_sec_640', 'value': B / (ms / 1e3), 'unit': UNIT,
+           'ms_per_step': ms, 'steps': K, 'nms_ms': nms_ms,
+           'detections_per_image': float(counts.float().mean()),
+           'roofline': {'bound': 'hbm', 'achieved': alg / 1e9 / (sum(r['ms'] for r in streaming) / 1e3),
+                        'frac': alg / 1e9 / (sum(r['ms'] for r in streaming) / 1e3) / peak,
+                        'note': 'forward kernels: algorithmic bytes of all launches / their summed time'},
+           'e2e': {'value': B / (ms_e2e / 1e3), 'unit': UNIT, 'ms_per_step': ms_e2e,
+                   'h2d_bytes_per_step': himg.numel() * 4,
+                   'd2h_bytes_per_step': hdets.numel() * 4 + hcnt.numel() * 4}}
+    del eng, img, himg, hdets
+    torch.cuda.empty_cache()
+    if cpu:
+        r = cpu_reference_infer(arch, 8, S, steps=3, warmup=1)
+        out['cpu_baseline'] = {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'port',
+                               'sample': f'8 images/step x 3 steps of the oracle simple_test '
+                                         f'(eval forward + decode + NMS) at {S}x{S}, torch CPU, '
+                                         f'{r["threads"]} threads', 'ms_per_step': r['ms_per_step']}
+    return out
+
+
+def plugin_e2e(arch, B, S, dev, steps, warmup):
+    """The same training step through the mmdet plugin surface (``plugins.YuNet.train_step`` +
+    ``torch.optim.SGD``), host buffers, H2D of images / GT lists and D2H of the losses per step."""
+    from libfacedetection.train_b200 import plugins, synthetic
+    cfg = dict(
+        type='YuNet',
+        backbone=dict(type='YuNetBackbone', stage_channels=plugins_arch(arch)['stage_channels'],
+                      downsample_idx=[0, 2, 3, 4], out_idx=[3, 4, 5]),
+        neck=dict(type='TFPN', in_channels=[64, 64, 64], out_idx=[0, 1, 2]),
+        bbox_head=dict(type='YuNet_Head', num_classes=1, in_channels=64,
+                       shared_stacked_convs=plugins_arch(arch)['shared_stacked_convs'], stacked_convs=0,
+                       feat_channels=64,
+                       prior_generator=dict(type='MlvlPointGenerator', offset=0, strides=[8, 16, 32]),
+                       loss_cls=dict(type='CrossEntropyLoss', use_sigmoid=True, reduction='sum', loss_weight=1.0),
+                       loss_bbox=dict(type='EIoULoss', loss_weight=5.0, reduction='sum'),
+                       use_kps=True, kps_num=5,
+                       loss_kps=dict(type='SmoothL1Loss', beta=0.1111111111111111, loss_weight=0.1),
+                       loss_obj=dict(type='CrossEntropyLoss', use_sigmoid=True, reduction='sum', loss_weight=1.0)),
+        train_cfg=dict(assigner=dict(type='SimOTAAssigner', center_radius=2.5)),
+        test_cfg=dict(nms_pre=-1, min_bbox_size=0, score_thr=0.02, nms=dict(type='nms', iou_threshold=0.45),
+                      max_per_img=-1))
+    torch.manual_seed(0)
+    m = plugins.DETECTORS.build(cfg).to(dev).train()
+    opt = torch.optim.SGD(m.parameters(), lr=LR, momentum=0.9, weight_decay=0.0005)
+    himg = torch.from_numpy(synthetic.make_images(B, S, 0)).pin_memory()
+    gb, gl, gk = synthetic.make_gt(B, S, 0)
+    hb = [torch.from_numpy(x).pin_memory() for x in gb]
+    hl = [torch.from_numpy(x) for x in gl]
+    hk = [torch.from_numpy(x).pin_memory() for x in gk]
+    bb_all, kp_all = torch.cat(hb).pin_memory(), torch.cat(hk).pin_memory()
+    lb_all = torch.cat(hl).pin_memory()
+    counts = [int(x.shape[0]) for x in hb]
+    dimg = torch.empty_like(himg, device=dev)
+
+    def step():
+        dimg.copy_(himg, non_blocking=True)
+        db = bb_all.to(dev, non_blocking=True).split(counts)
+        dk = kp_all.to(dev, non_blocking=True).split(counts)
+        dl = lb_all.to(dev, non_blocking=True).split(counts)
+        data = dict(img=dimg, img_metas=[{}] * B, gt_bboxes=list(db), gt_labels=list(dl),
+                    gt_keypointss=list(dk))
+        opt.zero_grad()
+        out = m.train_step(data)              # log_vars: host floats (D2H of the four losses)
+        out['loss'].backward()
+        opt.step()
+        return out
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    h2d = himg.numel() * 4 + bb_all.numel() * 4 + kp_all.numel() * 4 + lb_all.numel() * 8
+    del m, opt, dimg
+    torch.cuda.empty_cache()
+    return {'value': B / (ms / 1e3), 'unit': UNIT, 'ms_per_step': ms, 'steps': steps,
+            'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 16,
+            'api': 'plugins.YuNet.train_step + loss.backward() + torch.optim.SGD.step (mmdet plugin surface)'}
+
+
+def plugins_arch(arch):
+    from libfacedetection.train_b200.engine import ARCHS
+    return ARCHS[arch]
+
+
 def run_reference(args):
+    # nothing of the product is imported here: oracle/ + the stand-alone synthetic generator only
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
@@ -217,20 +455,45 @@ def run_ours(args):
     for d, h in zip(devb, host):
         for a, b_ in zip(d, h):
             a.copy_(b_)
+    # eager launches first (they also count the kernels of one step), then the CUDA-graph replay of the
+    # same step (engine.train_step_graph: one cudaGraphLaunch per iteration, lr as a device scalar)
     for i in range(Wm):
         eng.train_step(*devb[i % 2], lr=LR)
     sync_all()
+    l0 = lib.yunet_launch_count(eng.h)
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for i in range(max(4, K // 4)):
+        eng.train_step(*devb[i % 2], lr=LR)
+    g1.record()
+    sync_all()
+    ms_eager = max_over_ranks(g0.elapsed_time(g1)) / max(4, K // 4)
+    launches_per_step = int(lib.yunet_launch_count(eng.h) - l0) // max(4, K // 4)
+    step_fn, graph_info = eng.train_step, {'used': False, 'eager_ms_per_step': ms_eager,
+                                           'kernel_launches_per_step': launches_per_step}
+    if not args.no_graph:
+        try:
+            for i in range(6):             # per input slot: eager, capture, replay
+                eng.train_step_graph(*devb[i % 2], lr=LR)
+            sync_all()
+            step_fn = eng.train_step_graph
+            graph_info['used'] = True
+        except Exception as ex:            # e.g. a collective that cannot be captured: stay eager
+            graph_info['error'] = repr(ex)[:200]
+    for i in range(Wm):
+        step_fn(*devb[i % 2], lr=LR)
+    sync_all()
     sampler = ClockSampler(local)
     sampler.start()
-    l0 = lib.yunet_launch_count(eng.h)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(K):
-        losses = eng.train_step(*devb[i % 2], lr=LR)
+        losses = step_fn(*devb[i % 2], lr=LR)
     e1.record()
     sync_all()
-    launches = int(lib.yunet_launch_count(eng.h) - l0)
+    launches = launches_per_step * K       # kernels executed in the timed region (graph nodes or launches)
     ms_dev = max_over_ranks(e0.elapsed_time(e1)) / K
+    graph_info['ms_per_step'] = ms_dev
     clocks = sampler.stop()
     loss_vals = losses.cpu().numpy().tolist()
 
@@ -254,7 +517,7 @@ def run_ours(args):
             if i + 1 < n:
                 prefetch((i + 1) % 2)
             main.wait_event(copied[slot])
-            ls = eng.train_step(*devb[slot], lr=LR)
+            ls = step_fn(*devb[slot], lr=LR)
             consumed[slot].record(main)
             loss_host[slot].copy_(ls, non_blocking=True)
 
@@ -293,6 +556,29 @@ def run_ours(args):
             k[2] += 1
     if world > 1:
         dist.barrier()
+
+    # ---------------- the two collectives of the step, timed alone (device time, max over ranks)
+    comm = None
+    if world > 1:
+        from libfacedetection.train_b200 import dist_utils
+        scal = torch.ones(1, device=dev)
+        for _ in range(5):
+            dist_utils.reduce_mean_(scal)
+            dist_utils.allreduce_bucket_(eng.grads)
+        sync_all()
+        c0, c1, c2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        c0.record()
+        for _ in range(20):
+            dist_utils.reduce_mean_(scal)
+        c1.record()
+        for _ in range(20):
+            dist_utils.allreduce_bucket_(eng.grads)
+        c2.record()
+        sync_all()
+        comm = {'num_pos_allreduce_ms': max_over_ranks(c0.elapsed_time(c1)) / 20,
+                'grad_bucket_allreduce_ms': max_over_ranks(c1.elapsed_time(c2)) / 20,
+                'bucket_bytes': int(eng.grads.numel() * 4),
+                'note': 'back-to-back launches of each collective alone (latency bound)'}
 
     if rank != 0:
         if world > 1:
@@ -334,12 +620,33 @@ def run_ours(args):
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        r = cpu_reference_steps(args.arch, args.cpu_sample, S, steps=2, warmup=1)
+        r = cpu_reference_steps(args.arch, args.cpu_sample, S, steps=5, warmup=1)
         cpu = {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'port',
-               'sample': f'{args.cpu_sample} images/step, 2 timed steps of the oracle train step '
+               'sample': f'{args.cpu_sample} images/step, 5 timed steps of the oracle train step '
                          f'(fwd+SimOTA+loss+bwd+SGD), torch CPU, best thread count of those probed '
                          f'up to {r["cores"]} host cores (used {r["threads"]})',
                'ms_per_step': r['ms_per_step']}
+
+    # ---------------- the other BASELINE configs and the plugin-surface step, same process (N = 1)
+    extra, e2e_plugin = None, None
+    if world == 1 and not args.no_extra:
+        free_cache = torch.cuda.empty_cache
+        del eng
+        free_cache()
+        try:
+            e2e_plugin = plugin_e2e(args.arch, B, S, dev, steps=max(5, K // 2), warmup=3)
+        except Exception as ex:      # reported, never fatal for the headline line
+            e2e_plugin = {'error': repr(ex)[:300]}
+        extra = {}
+        try:
+            extra['yunet_s_train_320_bs256'] = extra_train_config('yunet_s', 256, 320, dev, peak)
+        except Exception as ex:
+            extra['yunet_s_train_320_bs256'] = {'error': repr(ex)[:300]}
+        try:
+            extra['yunet_n_infer_640_bs512'] = extra_infer_config('yunet_n', 512, 640, dev, peak,
+                                                                   cpu=not args.no_cpu_baseline)
+        except Exception as ex:
+            extra['yunet_n_infer_640_bs512'] = {'error': repr(ex)[:300]}
 
     gimg = B * world
     line = {
@@ -358,6 +665,10 @@ def run_ours(args):
         'clocks': clocks,
         'roofline': roofline,
         'cpu_baseline': cpu,
+        'cuda_graph': graph_info,
+        'e2e_plugin': e2e_plugin,
+        'comm_ms': comm,
+        'extra_configs': extra,
         'losses_last_step': loss_vals,
         'kernels_top': table[:6],
     }

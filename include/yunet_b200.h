@@ -129,6 +129,16 @@ int yunet_simota_assign(yunet_ctx* ctx, const yunet_loss_cfg* lc, const float* p
                         int* assigned_gt, float* matched_iou, float* counters, void* ws,
                         size_t ws_bytes, void* stream);
 
+/* SimOTAAssigner.assign for ONE image with explicit inputs (sim_ota_assigner.py:38-93, as called by
+ * yunet_head.py:575-577): scores (P) = sigmoid(cls)*sigmoid(obj), priors (P,4) = [cx, cy, stride_w,
+ * stride_h] already offset by half a stride, decoded_boxes (P,4) xyxy, gt (G,19) rows (only the
+ * box columns 0..3 are read), gt_offsets = {0, G}.  Outputs as yunet_simota_assign with B = 1.
+ * ws: P * 32 bytes of scratch when P > 2112 (NULL otherwise). */
+int yunet_simota_assign_ext(yunet_ctx* ctx, const yunet_loss_cfg* lc, int P, const float* scores,
+                            const float* priors, const float* decoded_boxes, const float* gt,
+                            const int* gt_offsets, int* assigned_gt, float* matched_iou,
+                            float* counters, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- losses + d(loss)/d(preds) --------------------------------------------------------------
  * num_total_samples: device pointer to 1 float = reduce_mean(num_pos) over ranks BEFORE the
  * max(.,1) clamp (the caller all-reduces counters[0] and divides by world size; single process:
@@ -151,6 +161,13 @@ int yunet_backward(yunet_ctx* ctx, const float* img, const float* params, const 
 int yunet_sgd_step(yunet_ctx* ctx, float* params, const float* grad_bucket, float* momentum_buf,
                    long long n, float lr, float momentum, float weight_decay, float grad_scale,
                    void* stream);
+
+/* the same step with the learning rate read from device memory (1 float): every launch parameter of
+ * a training iteration is then constant, so the iteration can be captured once and replayed as a
+ * CUDA graph while the LR schedule (configs/yunet_n.py:4-11) changes lr per iteration */
+int yunet_sgd_step_dev(yunet_ctx* ctx, float* params, const float* grad_bucket, float* momentum_buf,
+                       long long n, const float* lr_dev, float momentum, float weight_decay,
+                       float grad_scale, void* stream);
 
 /* ---- decode + score filter + NMS -------------------------------------------------------------
  * scale_factors: NULL or (B,4) device floats dividing the boxes (rescale=True).  dets:

@@ -70,10 +70,12 @@ def _load():
         'yunet_forward': (ci, [vp, vp, vp, vp, ci, ci, ci, ci, cf, vp, vp, cs, vp]),
         'yunet_assign_workspace_bytes': (cs, [vp, ci, ci, ci]),
         'yunet_simota_assign': (ci, [vp, P(LossCfg), vp, vp, vp, ci, ci, ci, vp, vp, vp, vp, cs, vp]),
+        'yunet_simota_assign_ext': (ci, [vp, P(LossCfg), ci, vp, vp, vp, vp, vp, vp, vp, vp, vp, cs, vp]),
         'yunet_loss_grad': (ci, [vp, P(LossCfg), vp, vp, vp, vp, vp, vp, vp, P(cf), ci, ci, ci,
                                  vp, vp, vp]),
         'yunet_backward': (ci, [vp, vp, vp, vp, ci, ci, ci, vp, vp, cs, vp]),
         'yunet_sgd_step': (ci, [vp, vp, vp, vp, ll, cf, cf, cf, cf, vp]),
+        'yunet_sgd_step_dev': (ci, [vp, vp, vp, vp, ll, vp, cf, cf, cf, vp]),
         'yunet_nms_workspace_bytes': (cs, [vp, ci, ci, ci]),
         'yunet_decode_nms': (ci, [vp, vp, ci, ci, ci, cf, cf, vp, ci, vp, vp, vp, vp, cs, vp]),
         'yunet_preprocess_u8': (ci, [vp, vp, vp, vp, vp, ci, ci, cf, vp, vp]),

@@ -395,6 +395,23 @@ int yunet_simota_assign(yunet_ctx* ctx, const yunet_loss_cfg* lc, const float* p
                    "simota_assign");
 }
 
+int yunet_simota_assign_ext(yunet_ctx* ctx, const yunet_loss_cfg* lc, int P, const float* scores,
+                            const float* priors, const float* decoded_boxes, const float* gt,
+                            const int* gt_offsets, int* assigned_gt, float* matched_iou,
+                            float* counters, void* ws, size_t ws_bytes, void* stream) {
+  if (!ctx || !lc || !scores || !priors || !decoded_boxes || !gt || !gt_offsets || !assigned_gt ||
+      !matched_iou || !counters)
+    return fail(ctx, -1, "simota_assign_ext: null pointer");
+  if (P <= 0) return fail(ctx, -2, "simota_assign_ext: bad prior count");
+  if (lc->candidate_topk < 1 || lc->candidate_topk > 10) return fail(ctx, -2, "simota_assign_ext: candidate_topk must be in 1..10");
+  const size_t need = simota_workspace_bytes(1, P);
+  if (need > 0 && (!ws || ws_bytes < need)) return fail(ctx, -3, "simota_assign_ext: workspace too small");
+  Scope sc(ctx, (cudaStream_t)stream, "simota_assign_ext");
+  return cuda_fail(ctx, launch_simota_assign_ext(to_dev(lc), P, scores, priors, decoded_boxes, gt, gt_offsets,
+                                                 assigned_gt, matched_iou, counters, ws, (cudaStream_t)stream),
+                   "simota_assign_ext");
+}
+
 int yunet_loss_grad(yunet_ctx* ctx, const yunet_loss_cfg* lc, const float* preds, const float* gt,
                     const int* gt_offsets, const int* assigned_gt, const float* matched_iou,
                     const float* counters, const float* num_total_samples, const float* loss_scale,
@@ -515,6 +532,15 @@ int yunet_sgd_step(yunet_ctx* ctx, float* params, const float* grad_bucket, floa
   Scope sc(ctx, (cudaStream_t)stream, "sgd_step");
   return cuda_fail(ctx, launch_sgd(params, grad_bucket, momentum_buf, n, lr, momentum, weight_decay,
                                    grad_scale, (cudaStream_t)stream), "sgd_step");
+}
+
+int yunet_sgd_step_dev(yunet_ctx* ctx, float* params, const float* grad_bucket, float* momentum_buf,
+                       long long n, const float* lr_dev, float momentum, float weight_decay,
+                       float grad_scale, void* stream) {
+  if (!params || !grad_bucket || !momentum_buf || !lr_dev || n <= 0) return fail(ctx, -1, "sgd_step_dev: bad arguments");
+  Scope sc(ctx, (cudaStream_t)stream, "sgd_step");
+  return cuda_fail(ctx, launch_sgd_dev(params, grad_bucket, momentum_buf, n, lr_dev, momentum, weight_decay,
+                                       grad_scale, (cudaStream_t)stream), "sgd_step_dev");
 }
 
 size_t yunet_nms_workspace_bytes(const yunet_ctx* ctx, int B, int H, int W) {

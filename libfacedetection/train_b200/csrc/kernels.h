@@ -148,6 +148,10 @@ cudaError_t launch_simota_assign(const yunet_loss_cfg_dev& lc, const LevelGeom& 
                                  const float* preds, const float* gt, const int* gt_offsets, int B,
                                  int* assigned, float* matched_iou, float* counters, void* ws,
                                  cudaStream_t s);
+cudaError_t launch_simota_assign_ext(const yunet_loss_cfg_dev& lc, int P, const float* scores,
+                                     const float* priors, const float* boxes, const float* gt,
+                                     const int* gt_offsets, int* assigned, float* matched_iou,
+                                     float* counters, void* ws, cudaStream_t s);
 size_t simota_workspace_bytes(int B, int P);
 cudaError_t launch_loss_grad(const yunet_loss_cfg_dev& lc, const LevelGeom& g, const float* preds,
                              const float* gt, const int* gt_offsets, const int* assigned,
@@ -164,6 +168,8 @@ cudaError_t launch_decode_nms(const LevelGeom& g, const float* preds, int B, flo
 // ---- sgd.cu ----
 cudaError_t launch_preprocess_u8(const unsigned char* pixels, const long long* offsets, const int* hw,
                                  const int* crop, int B, int S, float pad, float* out, cudaStream_t s);
+cudaError_t launch_sgd_dev(float* params, const float* grad, float* mom, long long n, const float* lr_dev,
+                           float momentum, float wd, float grad_scale, cudaStream_t s);
 cudaError_t launch_sgd(float* params, const float* grad, float* mom, long long n, float lr,
                        float momentum, float wd, float grad_scale, cudaStream_t s);
 

@@ -17,7 +17,28 @@ __global__ void sgd_kernel(float* __restrict__ w, const float* __restrict__ g, f
   v[i] = vi;
   w[i] = wi - lr * vi;
 }
+// same update with the learning rate read from device memory: the launch parameters stay constant, so
+// the whole training step can be replayed as a CUDA graph while the schedule changes lr per iteration
+__global__ void sgd_kernel_dev(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ v,
+                               long long n, const float* __restrict__ lr_dev, float momentum, float wd,
+                               float gscale) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float lr = __ldg(lr_dev);
+  const float wi = w[i];
+  const float gi = fmaf(wd, wi, g[i] * gscale);
+  const float vi = fmaf(momentum, v[i], gi);
+  v[i] = vi;
+  w[i] = wi - lr * vi;
+}
 }  // namespace
+
+cudaError_t launch_sgd_dev(float* params, const float* grad, float* mom, long long n, const float* lr_dev,
+                           float momentum, float wd, float grad_scale, cudaStream_t s) {
+  const int blocks = (int)((n + 255) / 256);
+  sgd_kernel_dev<<<blocks, 256, 0, s>>>(params, grad, mom, n, lr_dev, momentum, wd, grad_scale);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_sgd(float* params, const float* grad, float* mom, long long n, float lr,
                        float momentum, float wd, float grad_scale, cudaStream_t s) {

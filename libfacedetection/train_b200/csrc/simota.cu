@@ -14,6 +14,7 @@
 //   SmoothL1 landmarks (losses/smooth_l1_loss.py:24-32, losses/utils.py:42-59), plus
 //   d(loss)/d(preds) in the same pass.
 #include <cfloat>
+#include <cstring>
 #include <cstdio>
 
 #include "kernels.h"
@@ -109,10 +110,28 @@ __device__ __forceinline__ void decode_box(const float* pr, float px, float py, 
   x2 = __fadd_rn(cx, hw); y2 = __fadd_rn(cy, hh);
 }
 
+// Explicit per-prior inputs of SimOTAAssigner.assign (sim_ota_assigner.py:38-93): scores (P) =
+// sigmoid(cls)*sigmoid(obj) as the head passes them, priors (P,4) = [cx, cy, stride_w, stride_h]
+// already offset by half a stride (yunet_head.py:570-573; stride_w is used for both axes, they are
+// equal in every YuNet level), decoded boxes (P,4).  EXT = false derives all three from `preds`.
+struct AssignExt { const float* scores; const float* priors; const float* boxes; };
+
+template <bool EXT>
 __global__ void __launch_bounds__(NT) simota_assign_kernel(
     const yunet_loss_cfg_dev lc, const LevelGeom geo, const float* __restrict__ preds,
     const float* __restrict__ gt, const int* __restrict__ gt_offsets, int* __restrict__ assigned,
-    float* __restrict__ matched_iou, float* counters, Cand* gscratch, int vcap) {
+    float* __restrict__ matched_iou, float* counters, Cand* gscratch, int vcap, const AssignExt ext) {
+  // centre of prior p as the assigner sees it (offset prior) and its stride
+  auto offset_prior = [&](int p, float& ox, float& oy, float& s) {
+    if (EXT) {
+      ox = __ldg(ext.priors + 4 * p); oy = __ldg(ext.priors + 4 * p + 1); s = __ldg(ext.priors + 4 * p + 2);
+    } else {
+      float px, py;
+      prior_of(geo, p, px, py, s);
+      ox = __fadd_rn(px, __fmul_rn(s, 0.5f));   // yunet_head.py:572-573
+      oy = __fadd_rn(py, __fmul_rn(s, 0.5f));
+    }
+  };
   extern __shared__ float4 smem_raw[];
   Cand* scand = reinterpret_cast<Cand*>(smem_raw);                       // [vcap]
   unsigned char* sflag = reinterpret_cast<unsigned char*>(scand + vcap); // [P]
@@ -134,10 +153,8 @@ __global__ void __launch_bounds__(NT) simota_assign_kernel(
   // ---- pass A: validity flag per prior, zero the outputs
   int nvalid_local = 0;
   for (int p = tid; p < P; p += NT) {
-    float px, py, s;
-    prior_of(geo, p, px, py, s);
-    const float ox = __fadd_rn(px, __fmul_rn(s, 0.5f));   // yunet_head.py:572-573
-    const float oy = __fadd_rn(py, __fmul_rn(s, 0.5f));
+    float ox, oy, s;
+    offset_prior(p, ox, oy, s);
     bool any_gt = false, any_ct = false;
     for (int g = 0; g < G; ++g) {
       bool ig, ic;
@@ -180,14 +197,22 @@ __global__ void __launch_bounds__(NT) simota_assign_kernel(
     for (int w = 0; w < warp; ++w) off += s_warp[w];
     if (v) {
       const int slot = off + __popc(m & ((1u << lane) - 1u));
-      float px, py, s;
-      prior_of(geo, p, px, py, s);
-      const float* pr = pb + (long long)p * PC;
       Cand c;
-      decode_box(pr, px, py, s, c.x1, c.y1, c.x2, c.y2);
-      // yunet_head.py:576: cls.sigmoid() * obj.sigmoid(); sim_ota_assigner.py:160-165: BCE of
-      // sqrt(score) against the one-hot label (= 1), torch clamps log at -100
-      const float sc = __fmul_rn(sigmoid_ref(pr[0]), sigmoid_ref(pr[5]));
+      float sc;
+      if (EXT) {
+        c.x1 = __ldg(ext.boxes + 4 * p); c.y1 = __ldg(ext.boxes + 4 * p + 1);
+        c.x2 = __ldg(ext.boxes + 4 * p + 2); c.y2 = __ldg(ext.boxes + 4 * p + 3);
+        sc = __ldg(ext.scores + p);
+      } else {
+        float px, py, s;
+        prior_of(geo, p, px, py, s);
+        const float* pr = pb + (long long)p * PC;
+        decode_box(pr, px, py, s, c.x1, c.y1, c.x2, c.y2);
+        // yunet_head.py:576: cls.sigmoid() * obj.sigmoid()
+        sc = __fmul_rn(sigmoid_ref(pr[0]), sigmoid_ref(pr[5]));
+      }
+      // sim_ota_assigner.py:160-165: BCE of sqrt(score) against the one-hot label (= 1), torch
+      // clamps log at -100
       c.cls_cost = -fmaxf(logf(sqrtf(sc)), -100.0f);
       c.idx = p;
       c.cnt = 0;
@@ -214,11 +239,10 @@ __global__ void __launch_bounds__(NT) simota_assign_kernel(
     for (int v = lane; v < V; v += 32) {
       const Cand c = cand[v];
       const float iou = pair_iou(c.x1, c.y1, c.x2, c.y2, gb);
-      float px, py, s;
-      prior_of(geo, c.idx, px, py, s);
+      float ox, oy, s;
+      offset_prior(c.idx, ox, oy, s);
       bool ig, ic;
-      in_flags(__fadd_rn(px, __fmul_rn(s, 0.5f)), __fadd_rn(py, __fmul_rn(s, 0.5f)), s,
-               lc.center_radius, gb, ig, ic);
+      in_flags(ox, oy, s, lc.center_radius, gb, ig, ic);
       const float cost = pair_cost(lc, c.cls_cost, iou, ig && ic);
       if (iou > ti[KTOP - 1]) {
         ti[KTOP - 1] = iou;
@@ -281,9 +305,8 @@ __global__ void __launch_bounds__(NT) simota_assign_kernel(
     if (c.cnt == 0) continue;
     int gsel = c.gsel;
     if (c.cnt > 1) {
-      float px, py, s;
-      prior_of(geo, c.idx, px, py, s);
-      const float ox = __fadd_rn(px, __fmul_rn(s, 0.5f)), oy = __fadd_rn(py, __fmul_rn(s, 0.5f));
+      float ox, oy, s;
+      offset_prior(c.idx, ox, oy, s);
       float best = FLT_MAX;
       for (int g = 0; g < G; ++g) {
         const float4 gb = load_gt_box(gtb, g);
@@ -467,12 +490,37 @@ cudaError_t launch_simota_assign(const yunet_loss_cfg_dev& lc, const LevelGeom& 
   const size_t smem = (size_t)vcap * sizeof(Cand) + ((g.P + 15) & ~15);
   static size_t configured = 0;
   if (smem > configured) {
-    e = cudaFuncSetAttribute(simota_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(simota_assign_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured = smem;
   }
-  simota_assign_kernel<<<B, NT, smem, s>>>(lc, g, preds, gt, gt_offsets, assigned, matched_iou,
-                                           counters, reinterpret_cast<Cand*>(ws), vcap);
+  simota_assign_kernel<false><<<B, NT, smem, s>>>(lc, g, preds, gt, gt_offsets, assigned, matched_iou,
+                                                  counters, reinterpret_cast<Cand*>(ws), vcap, AssignExt{});
+  return cudaGetLastError();
+}
+
+// One image, explicit scores / offset priors / decoded boxes (the SimOTAAssigner.assign surface).
+cudaError_t launch_simota_assign_ext(const yunet_loss_cfg_dev& lc, int P, const float* scores,
+                                     const float* priors, const float* boxes, const float* gt,
+                                     const int* gt_offsets, int* assigned, float* matched_iou,
+                                     float* counters, void* ws, cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(counters, 0, 4 * sizeof(float), s);
+  if (e != cudaSuccess) return e;
+  LevelGeom g;
+  memset(&g, 0, sizeof g);
+  g.P = P;
+  const int vcap = P <= 2112 ? P : 6400;
+  const size_t smem = (size_t)vcap * sizeof(Cand) + ((P + 15) & ~15);
+  if (smem > 227 * 1024) return cudaErrorInvalidValue;
+  static size_t configured = 0;
+  if (smem > configured) {
+    e = cudaFuncSetAttribute(simota_assign_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  AssignExt ext{scores, priors, boxes};
+  simota_assign_kernel<true><<<1, NT, smem, s>>>(lc, g, nullptr, gt, gt_offsets, assigned, matched_iou,
+                                                 counters, reinterpret_cast<Cand*>(ws), vcap, ext);
   return cudaGetLastError();
 }
 

@@ -66,10 +66,11 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parit
 // try_wait returns after a few dozen cycles, so an un-throttled loop of waiting warps takes a third
 // of the SM's issue slots away from the working warps (measured: profiles/r2_*): back off with a
 // short nanosleep between polls.
-__device__ __forceinline__ bool mbar_wait_abort(uint64_t* bar, uint32_t parity, volatile int* abort_flag) {
+__device__ __forceinline__ bool mbar_wait_abort(uint64_t* bar, uint32_t parity, volatile int* abort_flag,
+                                                uint32_t sleep_ns = 40) {
   if (mbar_try_wait(bar, parity)) return true;
   for (uint32_t i = 0; i < (1u << 22); ++i) {
-    __nanosleep(40);
+    if (sleep_ns) __nanosleep(sleep_ns);
     if (mbar_try_wait(bar, parity)) return true;
     if ((i & 63u) == 63u && *abort_flag != 0) return false;
   }

@@ -24,7 +24,11 @@
 //   epilogue  the convert warps: tcgen05.ld, + bias (FADD2), zero outside the image -> y ring (2 slots).
 //   depthwise warp = 4 output columns, lane = channel pair; per block row 6 LDS.64, 3x3 stencil on
 //             the register window (FFMA2), z stored once (coalesced 256 B per pixel), BN statistics
-//             (fp32 per block, fp64 across blocks).
+//             (fp32 per block, fp64 across blocks).  Measured alternatives (tools/dw_bench.cu,
+//             tools/st_bench.cu, profiles/r2_*): the stage computes in 515 cycles per block but the
+//             30 KB of stores need ~1050 cycles of the SM's store path whatever the instruction
+//             (STG.64/128/256, cp.async.bulk); staging the row in shared memory + one bulk store per
+//             row behind a DW-wide barrier was slower (0.28 ms vs 0.20 ms for the 80x80 unit).
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -146,6 +150,11 @@ struct BlkIter {
 template <int COUT>
 __device__ __forceinline__ int y_swz(int col) { return COUT == 16 ? ((col >> 1) & 3) : (col & 7); }
 
+__device__ __forceinline__ bool elect_one() {
+  uint32_t p;
+  asm volatile("{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\tselp.u32 %0, 1, 0, pe;\n\t}" : "=r"(p));
+  return p != 0;
+}
 __device__ __forceinline__ float2 lds64(uint32_t addr) {
   float2 v;
   asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
@@ -170,7 +179,7 @@ __device__ __forceinline__ void sts128_xor(uint32_t A, uint32_t xr, uint32_t x, 
 
 #ifdef YUNET_WS_TIMING
 #define WT_DECL long long wt_t = clock64();
-#define WT(k) do { if (blockIdx.x == 0 && lane == 0 && CIN == 64 && COUT == 64 && MODE == 0 && a.H >= 80) { const long long t_ = clock64(); atomicAdd(status + 32 + (k), (int)(t_ - wt_t)); wt_t = t_; } } while (0)
+#define WT(k) do { if (blockIdx.x == 0 && (lane == 0 || warp == 1) && CIN == 64 && COUT == 64 && MODE == 0 && a.H >= 80) { const long long t_ = clock64(); atomicAdd(status + 32 + (k), (int)(t_ - wt_t)); wt_t = t_; } } while (0)
 #else
 #define WT_DECL
 #define WT(k)
@@ -251,7 +260,10 @@ unit_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap, const UnitFwdArgs a
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tbase = warp_uniform(*tmem_ptr);
+  // all 512 columns are allocated, so the allocation starts at TMEM address 0 (checked: a different
+  // base would only cost the uniform-register issue path, but the kernel relies on it being constant)
+  constexpr uint32_t tbase = 0;
+  if (tid == 0 && *tmem_ptr != 0) { atomicExch(status, 20); *abort_flag = 1; }
 
   // ---- this CTA's share of the global block sequence (+ one priming block inside a strip)
   const int g0 = (int)(((long long)blockIdx.x * geo.G) / gridDim.x);
@@ -280,36 +292,39 @@ unit_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap, const UnitFwdArgs a
     }
   } else if (warp == C::W_MMA) {
     // ================================================================= MMA issuer
+    // ONE elected thread runs the whole issue loop with warp-uniform operands only (TMEM base 0,
+    // shared-memory descriptors from the uniform dynamic-smem base): the compiler then keeps every
+    // descriptor in uniform registers and emits back-to-back UTCHMMA (1 instruction per MMA; with a
+    // per-instruction elect it was ~11 instructions and ~48 cycles per 32-cycle MMA)
     constexpr uint32_t idesc = make_idesc_tf32(128, COUT);
     const uint64_t dbhi = make_desc_sw128_kmajor(smem_u32(sBhi));
     const uint64_t dblo = make_desc_sw128_kmajor(smem_u32(sBlo));
-    bool ok = true;
-    for (int j = 0; j < nblk && ok; ++j) {
-      const int buf = j & 1;
-      const uint32_t par = (uint32_t)((j >> 1) & 1);
-      WT_DECL
-      if (!mbar_wait_abort(&bars[BAR_A_FULL + buf], par, abort_flag)) { if (lane == 0) atomicExch(status, 22); ok = false; }
-      if (ok && !mbar_wait_abort(&bars[BAR_D_EMPTY + buf], par ^ 1u, abort_flag)) { if (lane == 0) atomicExch(status, 23); ok = false; }
-      ok = __all_sync(0xffffffffu, ok);
-      WT(0);
-      if (ok) {
+    if (elect_one()) {
+      for (int j = 0; j < nblk; ++j) {
+        const int buf = j & 1;
+        const uint32_t par = (uint32_t)((j >> 1) & 1);
+        WT_DECL
+        if (!mbar_wait_abort(&bars[BAR_A_FULL + buf], par, abort_flag)) { atomicExch(status, 22); break; }
+        if (!mbar_wait_abort(&bars[BAR_D_EMPTY + buf], par ^ 1u, abort_flag)) { atomicExch(status, 23); break; }
+        WT(0);
         tc_fence_after();
-        const uint32_t dcol = tbase + COL_D + buf * 64;
-        const uint32_t ahi = tbase + COL_A + buf * 128, alo = ahi + CIN;
+        const uint32_t dcol = COL_D + buf * 64;
+        const uint32_t ahi = COL_A + buf * 128, alo = ahi + CIN;
         uint32_t acc = 0;
 #pragma unroll
         for (int pass = 0; pass < 3; ++pass) {
 #pragma unroll
           for (int k = 0; k < C::KS; ++k) {
             const uint32_t koff = ((k >> 2) * C::B_BLOCK + (k & 3) * 32) >> 4;
-            mma_tf32_ts_elect(dcol, (pass == 0 ? alo : ahi) + k * 8, (pass == 1 ? dblo : dbhi) + koff, idesc, acc);
+            mma_tf32_ts(dcol, (pass == 0 ? alo : ahi) + k * 8, (pass == 1 ? dblo : dbhi) + koff, idesc, acc);
             acc = 1;
           }
         }
-        mma_commit_elect(&bars[BAR_MMA_DONE + buf]);
+        mma_commit(&bars[BAR_MMA_DONE + buf]);
+        WT(1);
       }
-      WT(1);
     }
+    __syncwarp();
   } else if (warp >= C::W_CV && warp < C::W_CV + 4 * C::NG) {
     // ================================================================= convert + epilogue
     const int grp = (warp - C::W_CV) >> 2;              // ping-pong group: blocks j == grp (mod NG)

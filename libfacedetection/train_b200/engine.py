@@ -215,6 +215,28 @@ class YuNetEngine:
               'yunet_simota_assign')
         return assigned, miou, counters
 
+    def assign_ext(self, scores, priors, decoded_boxes, gt_boxes):
+        """``SimOTAAssigner.assign`` for one image with explicit inputs (sim_ota_assigner.py:38-93):
+        scores (P,) = sigmoid(cls)*sigmoid(obj), priors (P,4) offset ``[cx, cy, stride, stride]``,
+        decoded boxes (P,4), gt boxes (G,4); all fp32 CUDA.  Returns (assigned (P,) int32 with the
+        1-based gt index or 0, matched IoU (P,), counters)."""
+        P_ = int(scores.shape[0])
+        G = int(gt_boxes.shape[0])
+        gt = torch.zeros(max(G, 1), 19, device=self.device)
+        if G:
+            gt[:, :4] = gt_boxes
+        offs = torch.tensor([0, G], dtype=torch.int32, device=self.device)
+        assigned = torch.zeros(P_, dtype=torch.int32, device=self.device)
+        miou = torch.zeros(P_, device=self.device)
+        counters = torch.zeros(4, device=self.device)
+        aws = torch.empty(max(P_ * 32 if P_ > 2112 else 16, 16), dtype=torch.uint8, device=self.device)
+        check(self.h, lib.yunet_simota_assign_ext(
+            self.h, C.byref(self.loss_cfg), P_, _ptr(scores.contiguous().float()),
+            _ptr(priors.contiguous().float()), _ptr(decoded_boxes.contiguous().float()), _ptr(gt),
+            _ptr(offs), _ptr(assigned), _ptr(miou), _ptr(counters), _ptr(aws), aws.numel(), _stream()),
+            'yunet_simota_assign_ext')
+        return assigned, miou, counters
+
     def loss_grad(self, preds, gt, gt_offsets, assigned, miou, counters, num_total, H, W,
                   loss_scale=None, want_grad=True):
         B, P, _ = preds.shape
@@ -241,11 +263,41 @@ class YuNetEngine:
                                          _ptr(self.momentum_buf), self.ctx.num_params, lr, momentum,
                                          weight_decay, grad_scale, _stream()), 'yunet_sgd_step')
 
+    def train_step_graph(self, img, gt, gt_offsets, lr=0.01, momentum=0.9, weight_decay=0.0005):
+        """``train_step`` replayed as ONE CUDA graph: the whole iteration — forward,
+        SimOTA, [num_pos all-reduce], loss + gradient, backward, [bucket all-reduce], SGD — is
+        captured once per set of input buffers and relaunched with a single ``cudaGraphLaunch``;
+        the learning rate is a device scalar, so the schedule keeps working.  The first call with
+        new buffers runs eagerly (it also sizes every workspace), the second captures, later ones
+        replay.  Inputs must stay at the same addresses (a real input pipeline writes into fixed
+        device slots, like ``bench.py``'s two double-buffered ones)."""
+        key = (img.data_ptr(), gt.data_ptr(), gt_offsets.data_ptr(), tuple(img.shape), tuple(gt.shape),
+               float(momentum), float(weight_decay))
+        if not hasattr(self, '_graphs'):
+            self._graphs, self._lr_dev = {}, torch.zeros(1, device=self.device)
+        self._lr_dev.fill_(float(lr))
+        st = self._graphs.get(key)
+        if st is None:                      # first sight of these buffers: eager step
+            self._graphs[key] = 'seen'
+            return self._train_step_impl(img, gt, gt_offsets, None, momentum, weight_decay, True, lr_dev=self._lr_dev)
+        if st == 'seen':                    # second: capture (nothing executes), then fall through
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g):
+                out = self._train_step_impl(img, gt, gt_offsets, None, momentum, weight_decay, True,
+                                            lr_dev=self._lr_dev)
+            st = self._graphs[key] = (g, out)
+        st[0].replay()
+        return st[1]
+
     def train_step(self, img, gt, gt_offsets, lr=0.01, momentum=0.9, weight_decay=0.0005,
                    step=True):
         """One full training iteration on this rank: forward (train-mode BN) -> SimOTA ->
         [all-reduce num_pos] -> losses + d_preds -> backward -> [all-reduce gradient bucket] ->
         fused SGD.  Returns the device tensor of the four losses [cls, bbox, obj, kps]."""
+        return self._train_step_impl(img, gt, gt_offsets, lr, momentum, weight_decay, step)
+
+    def _train_step_impl(self, img, gt, gt_offsets, lr, momentum, weight_decay, step, lr_dev=None):
         from . import dist_utils
         B, _, H, W = img.shape
         preds = self.forward(img, train=True, preds=self._buf('preds', (B, self.ctx.num_priors(H, W), 16), torch.float32))
@@ -260,7 +312,12 @@ class YuNetEngine:
                                          H, W)
         self.backward(img, d_preds)
         grad_scale = dist_utils.allreduce_bucket_(self.grads)   # ONE all-reduce, 303 KB (yunet_n)
-        if step:
+        if step and lr_dev is not None:
+            check(self.h, lib.yunet_sgd_step_dev(self.h, _ptr(self.params), _ptr(self.grads),
+                                                 _ptr(self.momentum_buf), self.ctx.num_params, _ptr(lr_dev),
+                                                 momentum, weight_decay, grad_scale, _stream()),
+                  'yunet_sgd_step_dev')
+        elif step:
             self.sgd_step(lr, momentum, weight_decay, grad_scale)
         return losses
 

@@ -177,15 +177,21 @@ def prepare_test_image(img_u8, mode=0, divisor=32):
     """Host side of the reference's test pipeline (``configs/yunet_n.py:59-78`` as patched by
     ``tools/test_widerface.py:76-96``): mode 0 = keep-ratio resize into 640x640, mode > 30 = into
     (mode, mode), each followed by a zero pad to that size; mode 2 = original size padded to a
-    multiple of ``divisor`` (mode 1, 1100 x 1650, is not supported yet).  Returns the float32 CHW image (BGR, 0..255)
-    and the ``[w_scale, h_scale, w_scale, h_scale]`` float32 factor detections are divided by.
+    multiple of ``divisor``; mode 1 = keep-ratio resize into 1100 x 1650 (short x long side), padded
+    to the next multiple of ``divisor`` (the reference pads to exactly 1100 x 1650, a shape its own
+    TFPN cannot add: 1100 / 8 = 137 vs 2 * (1100 // 16) = 136).  Returns the float32 CHW image (BGR,
+    0..255) and the ``[w_scale, h_scale, w_scale, h_scale]`` float32 factor detections are divided by.
 
     Resizing uses ``cv2.resize`` on the uint8 image exactly like ``mmcv.imrescale`` (cv2 backend)."""
     h, w = img_u8.shape[:2]
     if mode == 1:
-        raise NotImplementedError('mode 1 (1100 x 1650) exceeds the 8 704 priors per image the NMS '
-                                  'kernel keeps in shared memory')
-    if mode == 2:
+        scale = min(1650 / max(h, w), 1100 / min(h, w))                 # mmcv.rescale_size((1100, 1650))
+        new_w, new_h = int(w * float(scale) + 0.5), int(h * float(scale) + 0.5)
+        import cv2
+        img = cv2.resize(img_u8, (new_w, new_h), interpolation=cv2.INTER_LINEAR)
+        factor = np.array([new_w / w, new_h / h, new_w / w, new_h / h], dtype=np.float32)
+        out_h, out_w = -(-new_h // divisor) * divisor, -(-new_w // divisor) * divisor
+    elif mode == 2:
         out_h, out_w = -(-h // divisor) * divisor, -(-w // divisor) * divisor
         img, factor = img_u8, np.ones(4, np.float32)
     else:

@@ -196,16 +196,70 @@ class TFPN(nn.Module):
         return feats
 
 
+class AssignResult:
+    """The fields of mmdet's ``AssignResult`` the YuNet head reads (assign_result.py): ``num_gts``,
+    ``gt_inds`` (P,) long, 1-based gt index or 0, ``max_overlaps`` (P,) matched IoU (-1e5 for
+    non-positives, all zero when nothing could be assigned), ``labels`` (P,) long or None."""
+
+    def __init__(self, num_gts, gt_inds, max_overlaps, labels=None):
+        self.num_gts = num_gts
+        self.gt_inds = gt_inds
+        self.max_overlaps = max_overlaps
+        self.labels = labels
+
+    @property
+    def num_preds(self):
+        return len(self.gt_inds)
+
+
 @BBOX_ASSIGNERS.register_module()
 class SimOTAAssigner:
-    """Hyper-parameter carrier (sim_ota_assigner.py:28-36); the assignment itself is the batched
-    ``yunet_simota_assign`` kernel invoked by the head for all images at once."""
+    """``mmdet/core/bbox/assigners/sim_ota_assigner.py:10-93``.  Inside the fused head the batched
+    ``yunet_simota_assign`` kernel assigns all images at once; ``assign`` is the reference's
+    per-image entry point (``yunet_head.py:575-577``) on the same kernel through
+    ``yunet_simota_assign_ext``, so a reference head that calls it keeps working."""
 
     def __init__(self, center_radius=2.5, candidate_topk=10, iou_weight=3.0, cls_weight=1.0):
         self.center_radius = center_radius
         self.candidate_topk = candidate_topk
         self.iou_weight = iou_weight
         self.cls_weight = cls_weight
+        self._engine = None
+
+    def _core(self, device):
+        if self._engine is None or self._engine.device != device:
+            lc = _capi.default_loss_cfg()
+            lc.center_radius = float(self.center_radius)
+            lc.candidate_topk = int(self.candidate_topk)
+            lc.iou_weight = float(self.iou_weight)
+            lc.cls_weight = float(self.cls_weight)
+            self._engine = YuNetEngine('yunet_n', device=device, loss_cfg=lc)
+        return self._engine
+
+    def assign(self, pred_scores, priors, decoded_bboxes, gt_bboxes, gt_labels,
+               gt_bboxes_ignore=None, eps=1e-7):
+        """pred_scores (P,1), priors (P,4) ``[cx, cy, stride_w, stride_h]`` (offset by half a
+        stride), decoded_bboxes (P,4), gt_bboxes (G,4), gt_labels (G,) -> ``AssignResult``."""
+        if pred_scores.dim() == 2 and pred_scores.shape[1] != 1:
+            raise NotImplementedError('the B200 SimOTA kernel is single-class (YuNet: num_classes=1)')
+        dev = decoded_bboxes.device
+        if dev.type != 'cuda':
+            raise RuntimeError('SimOTAAssigner.assign needs CUDA tensors (there is no CPU fallback)')
+        num_gt, P_ = int(gt_bboxes.shape[0]), int(decoded_bboxes.shape[0])
+        gt_inds = torch.zeros(P_, dtype=torch.long, device=dev)
+        labels = None if gt_labels is None else torch.full((P_,), -1, dtype=torch.long, device=dev)
+        if num_gt == 0 or P_ == 0:
+            return AssignResult(num_gt, gt_inds, torch.zeros(P_, device=dev), labels)
+        assigned, miou, counters = self._core(dev).assign_ext(pred_scores.reshape(-1), priors,
+                                                               decoded_bboxes, gt_bboxes)
+        gt_inds = assigned.long()
+        pos = gt_inds > 0
+        if not bool(pos.any()):      # no prior inside any gt box / centre region
+            return AssignResult(num_gt, gt_inds, torch.zeros(P_, device=dev), labels)
+        max_overlaps = torch.where(pos, miou, torch.full_like(miou, -100000.0))
+        if labels is not None:
+            labels[pos] = gt_labels[gt_inds[pos] - 1].long()
+        return AssignResult(num_gt, gt_inds, max_overlaps, labels)
 
 
 def _loss_weight(cfg, default):
@@ -367,9 +421,31 @@ class _FusedLoss(torch.autograd.Function):
             _, d_preds = core.loss_grad(preds, gt, offs, assigned, miou, counters, num_total, H, W,
                                         loss_scale=scale)
         core.backward(img, d_preds)
+        # every parameter gets a VIEW of the flat gradient bucket (no copies): autograd's
+        # AccumulateGrad adopts it as ``.grad`` when the gradient was None (zero_grad(set_to_none=True),
+        # torch's default) and adds it in place otherwise; the bucket is rewritten by the next backward
         views = core.param_views(core.grads)
-        grads = [views[k].clone() for k in glue.names]
+        grads = [views[k] for k in glue.names]
         return (None, None, None, None) + tuple(grads)
+
+
+def pack_gt_csr_device(gt_bboxes, gt_keypointss, device):
+    """Ragged per-image GT lists -> the CSR arrays of the C ABI, built ON THE DEVICE (the reference
+    hands the head device tensors; no ``.cpu()`` per step): gt (sumG, 19) fp32 rows
+    ``[x1,y1,x2,y2, kx0,ky0,..,kx4,ky4, w0..w4]`` and offsets (B+1,) int32.  The row counts come from
+    the tensor shapes, so nothing synchronises."""
+    counts = [int(b.shape[0]) for b in gt_bboxes]
+    offs = torch.tensor(np.concatenate([[0], np.cumsum(counts)]).astype(np.int32))
+    offs = offs.to(device, non_blocking=True)
+    total = int(sum(counts))
+    gt = torch.empty(max(total, 0), 19, device=device, dtype=torch.float32)
+    if total:
+        bb = torch.cat([b.reshape(-1, 4) for b in gt_bboxes]).to(device=device, dtype=torch.float32)
+        kp = torch.cat([k.reshape(-1, 5, 3) for k in gt_keypointss]).to(device=device, dtype=torch.float32)
+        gt[:, :4] = bb
+        gt[:, 4:14] = kp[:, :, :2].reshape(-1, 10)
+        gt[:, 14:19] = kp[:, :, 2]
+    return gt, offs
 
 
 class _Glue:
@@ -433,11 +509,7 @@ class _Glue:
 
     def losses(self, img, gt_bboxes, gt_keypointss):
         self.sync_from_modules()
-        gb = [g.detach().cpu().numpy() for g in gt_bboxes]
-        gk = [g.detach().cpu().numpy() for g in gt_keypointss]
-        gt, offs = synthetic.pack_gt_csr(gb, gk)
-        gt = torch.from_numpy(gt).to(img.device)
-        offs = torch.from_numpy(offs).to(img.device)
+        gt, offs = pack_gt_csr_device(gt_bboxes, gt_keypointss, img.device)
         l = _FusedLoss.apply(self, img.contiguous(), gt, offs, *self.params)
         for m in self.modules.values():
             for mod in m.modules():
@@ -446,18 +518,18 @@ class _Glue:
         return dict(loss_cls=l[0], loss_bbox=l[1], loss_obj=l[2], loss_kps=l[3])
 
 
-_GLUES = {}
 _ENGINES = {}
 
 
 def _engine_for(backbone, neck, head):
+    """The engine glue of a (backbone, neck, head) triple lives ON the head module (plain attribute,
+    not a sub-module), so it is freed with the model instead of accumulating in a global table."""
     if neck is None or head is None:
         raise RuntimeError('the fused path needs backbone, neck and head')
-    key = (id(backbone), id(neck), id(head))
-    g = _GLUES.get(key)
-    if g is None:
+    g = head.__dict__.get('_b200_glue')
+    if g is None or g.modules['backbone'] is not backbone or g.modules['neck'] is not neck:
         g = _Glue(backbone, neck, head)
-        _GLUES[key] = g
+        head.__dict__['_b200_glue'] = g
     return g
 
 

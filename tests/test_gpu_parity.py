@@ -212,6 +212,10 @@ def _oracle_grads(arch, img_np, gb, gl, gk, assigned, miou, dtype, masks=None):
     if masks is not None:
         print(f'   oracle({dtype}): {mo.overrides} ReLU and {mo.pool_overrides} max-pool decisions of '
               f'{mo.total} taken from the kernels')
+        # the masked oracle may follow the kernels only at genuinely rounding-fragile elements: a
+        # kernel that was systematically wrong near zero would need many overrides to pass
+        assert mo.overrides <= 1e-5 * mo.total + 8, (mo.overrides, mo.total)
+        assert mo.pool_overrides <= 1e-5 * mo.total + 8, (mo.pool_overrides, mo.total)
     orig = orc.simota_assign
     it = iter(range(len(gb)))
 
@@ -330,8 +334,17 @@ def test_train_step_matches_reference_golden(arch, seed):
                                     counters, size, size)
     eng.backward(img, d_preds)
     if not same_as_golden:
-        pytest.skip('assignment differs from the golden one only by cost ties; value parity is '
-                    'covered by test_loss_and_grads_match_oracle')
+        # tie-equivalent assignment (checked above): the golden losses / gradients belong to another
+        # tie order, so compare against the oracle forced onto THIS assignment instead of dropping out
+        img_np = synthetic.make_images(B, size, seed)
+        masks = _engine_masks(eng, B, size, size)
+        ref_losses, ref32 = _oracle_grads(arch, img_np, gb, gl, gk, assigned, miou, torch.float32, masks)
+        _, truth = _oracle_grads(arch, img_np, gb, gl, gk, assigned, miou, torch.float64, masks)
+        mine_l = losses.cpu().numpy()
+        for i, k in enumerate(('loss_cls', 'loss_bbox', 'loss_obj', 'loss_kps')):
+            assert abs(mine_l[i] - ref_losses[k]) <= TOL * max(1.0, abs(ref_losses[k])), k
+        _check_grads(arch, eng.param_views(eng.grads), ref32, truth)
+        return
     ref_l = g['losses']
     mine_l = losses.cpu().numpy()
     for i, k in enumerate(('loss_cls', 'loss_bbox', 'loss_obj', 'loss_kps')):
@@ -461,3 +474,165 @@ def test_full_size_properties_bs256():
     # (c) every image has >= 1 positive (each gt gets dynamic_k >= 1)
     a = eng._bufs[('assigned', (B, 2100), torch.int32)]
     assert int(((a > 0).sum(1) == 0).sum()) == 0
+
+
+# --------------------------------------------------------------------------------- hardening (round 2)
+def test_train_step_bs256_matches_oracle():
+    """Value parity AT the benchmarked size (yunet_n, 320x320, bs=256): train-mode BN statistics
+    accumulated over 256 images by 148 persistent CTAs, SimOTA on every image, the four losses, the
+    BN running statistics and the five largest parameter-gradient tensors against the fp32 oracle
+    (same assignment, same ReLU branch at rounding-fragile elements)."""
+    B, size, seed, arch = 256, 320, 3, 'yunet_n'
+    eng = _engine(arch)
+    img_np = synthetic.make_images(B, size, seed)
+    gb, gl, gk = synthetic.make_gt(B, size, seed)
+    img = torch.from_numpy(img_np).cuda()
+    preds = eng.forward(img, train=True)
+    exact, tie, (gt, offs, assigned, miou, counters) = _check_assignment(eng, preds, gb, gl, gk, size, size)
+    print(f'bs256: assignment exact {exact}/{B}, tie-equivalent {tie}')
+    assert exact + tie == B and exact >= 0.9 * B
+    losses, d_preds = eng.loss_grad(preds, gt, offs, eng._bufs[('assigned', (B, preds.shape[1]), torch.int32)],
+                                    eng._bufs[('miou', (B, preds.shape[1]), torch.float32)], counters,
+                                    counters, size, size)
+    eng.backward(img, d_preds)
+    masks = _engine_masks(eng, B, size, size)
+    P, Bf = _weights(arch)
+    Pg = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    Bf = {k: v.clone() for k, v in Bf.items()}
+    with _MaskedOracle(masks) as mo:
+        outs = orc.model_forward(torch.from_numpy(img_np), Pg, Bf, arch, training=True)
+    print(f'bs256: {mo.overrides} ReLU / {mo.pool_overrides} pool decisions of {mo.total} from the kernels')
+    assert mo.overrides <= 1e-5 * mo.total + 8 and mo.pool_overrides <= 1e-5 * mo.total + 8
+    f = orc.flatten_preds(*outs)
+    ref_preds = torch.cat([f[0], f[1], f[2].unsqueeze(-1), f[3]], -1)
+    assert _rel(preds, ref_preds) < TOL
+    orig, it = orc.simota_assign, iter(range(B))
+
+    def forced(*a, **k):
+        b = next(it)
+        return assigned[b].clone(), torch.where(assigned[b] > 0, miou[b], torch.full_like(miou[b], -1e5))
+
+    orc.simota_assign = forced
+    try:
+        ref_losses = orc.head_loss(*outs, [torch.from_numpy(x) for x in gb], [torch.from_numpy(x) for x in gl],
+                                   [torch.from_numpy(x) for x in gk])
+    finally:
+        orc.simota_assign = orig
+    mine_l = losses.cpu().numpy()
+    for i, k in enumerate(('loss_cls', 'loss_bbox', 'loss_obj', 'loss_kps')):
+        r = float(ref_losses[k])
+        assert abs(mine_l[i] - r) <= TOL * max(1.0, abs(r)), (k, mine_l[i], r)
+    sum(ref_losses.values()).backward()
+    ref_g = {k: v.grad.detach() for k, v in Pg.items()}
+    mine_g = eng.param_views(eng.grads)
+    gmax = max(float(v.abs().max()) for v in ref_g.values())
+    top5 = sorted(ref_g, key=lambda k: -float(ref_g[k].abs().max()))[:5]
+    for k in top5:
+        e = float((mine_g[k].cpu() - ref_g[k]).abs().max())
+        sc = float(ref_g[k].abs().max())
+        print(f'   grad {k:50s} err/scale {e / sc:.3e}')
+        assert e <= TOL_GRAD * sc + 1e-5 * gmax, (k, e, sc)
+    # BN running statistics after the step (momentum 0.1, unbiased variance), all 17 layers
+    eng.num_batches_tracked += 0
+    sd = eng.state_dict()
+    for k, v in Bf.items():
+        if v.dtype.is_floating_point:
+            assert _rel(sd[k], v) < TOL, k
+
+
+def _grid_faces(size, n_side, rng):
+    """n_side x n_side faces on a jittered grid: a crowd that makes almost every prior a candidate."""
+    cell = size / n_side
+    ys, xs = np.meshgrid(np.arange(n_side), np.arange(n_side), indexing='ij')
+    cx = (xs.reshape(-1) + 0.5) * cell + rng.uniform(-2, 2, n_side * n_side)
+    cy = (ys.reshape(-1) + 0.5) * cell + rng.uniform(-2, 2, n_side * n_side)
+    w = rng.uniform(0.7, 0.95, n_side * n_side) * cell
+    h = np.minimum(1.2 * w, cell * 0.98)
+    bb = np.stack([cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2], 1).astype(np.float32)
+    kp = np.empty((bb.shape[0], 5, 3), np.float32)
+    kp[:, :, 0] = bb[:, None, 0] + rng.uniform(0, 1, (bb.shape[0], 5)) * w[:, None]
+    kp[:, :, 1] = bb[:, None, 1] + rng.uniform(0, 1, (bb.shape[0], 5)) * h[:, None]
+    kp[:, :, 2] = (rng.uniform(0, 1, bb.shape[0]) < 0.5).astype(np.float32)[:, None]
+    return bb, np.zeros(bb.shape[0], np.int64), kp
+
+
+def test_simota_and_loss_at_640_with_a_crowd():
+    """8 400 priors per image (640x640) and a crowded image (400 faces, more candidates than the
+    shared-memory candidate buffer holds -> the global-scratch path of simota_assign_kernel):
+    assignment index-exact (or cost-tie equivalent) and losses against the oracle."""
+    size, arch = 640, 'yunet_n'
+    eng = _engine(arch)
+    rng = np.random.default_rng(5)
+    gb, gl, gk = synthetic.make_gt(2, size, 9, max_faces=64)
+    cb, cl, ck = _grid_faces(size, 20, rng)
+    gb.append(cb); gl.append(cl); gk.append(ck)
+    B = 3
+    img_np = synthetic.make_images(B, size, 9)
+    img = torch.from_numpy(img_np).cuda()
+    preds = eng.forward(img, train=True)
+    assert preds.shape[1] == 8400
+    exact, tie, (gt, offs, assigned, miou, counters) = _check_assignment(eng, preds, gb, gl, gk, size, size)
+    print(f'640 + crowd: exact {exact}/{B}, tie-equivalent {tie}; positives per image '
+          f'{[(int((assigned[b] > 0).sum())) for b in range(B)]}')
+    # the crowd image really exceeds the shared-memory candidate capacity (6400)
+    pc = preds[2].cpu()
+    priors = torch.cat(orc.grid_priors([(size // s, size // s) for s in (8, 16, 32)], (8, 16, 32)))
+    off_pri = torch.cat([priors[:, :2] + priors[:, 2:] * 0.5, priors[:, 2:]], -1)
+    valid, _ = orc.in_gt_and_in_center(off_pri, torch.from_numpy(cb))
+    assert int(valid.sum()) > 6400, int(valid.sum())
+    losses, _ = eng.loss_grad(preds, gt, offs, eng._bufs[('assigned', (B, 8400), torch.int32)],
+                              eng._bufs[('miou', (B, 8400), torch.float32)], counters, counters, size, size)
+    P, Bf = _weights(arch)
+    with torch.no_grad():
+        outs = orc.model_forward(torch.from_numpy(img_np), P, {k: v.clone() for k, v in Bf.items()}, arch,
+                                 training=True)
+    orig, it = orc.simota_assign, iter(range(B))
+
+    def forced(*a, **k):
+        b = next(it)
+        return assigned[b].clone(), torch.where(assigned[b] > 0, miou[b], torch.full_like(miou[b], -1e5))
+
+    orc.simota_assign = forced
+    try:
+        ref = orc.head_loss(*outs, [torch.from_numpy(x) for x in gb], [torch.from_numpy(x) for x in gl],
+                            [torch.from_numpy(x) for x in gk])
+    finally:
+        orc.simota_assign = orig
+    mine_l = losses.cpu().numpy()
+    for i, k in enumerate(('loss_cls', 'loss_bbox', 'loss_obj', 'loss_kps')):
+        r = float(ref[k])
+        assert abs(mine_l[i] - r) <= TOL * max(1.0, abs(r)), (k, mine_l[i], r)
+
+
+def test_nms_beyond_the_shared_memory_prior_cap():
+    """Origin-size evaluation inputs (WIDER test modes 1 / 2): 1088 x 1664 -> 37 128 priors per
+    image, the global-scratch variant of decode_nms_kernel, against the oracle's get_bboxes."""
+    eng = _engine('yunet_n')
+    H, W = 1088, 1664
+    torch.manual_seed(3)
+    img = (torch.rand(2, 3, H, W) * 255)
+    dets, counts, kps = eng.detect(img.cuda(), score_thr=0.02, iou_thr=0.45, with_kps=True)
+    P, Bf = _weights('yunet_n')
+    with torch.no_grad():
+        outs = orc.model_forward(img, P, Bf, 'yunet_n', training=False)
+        ref = orc.get_bboxes(*outs)
+    assert eng.ctx.num_priors(H, W) == 136 * 208 + 68 * 104 + 34 * 52
+    for b in range(2):
+        n = int(counts[b])
+        rd = ref[b][0].numpy()
+        assert n == rd.shape[0], (n, rd.shape)
+        if n:
+            mine = dets[b, :n].cpu().numpy()
+            assert bool((mine[:-1, 4] >= mine[1:, 4]).all())
+            key = lambda d: d[np.lexsort((d[:, 1], d[:, 0]))]      # noqa: E731
+            np.testing.assert_allclose(key(mine), key(rd), rtol=1e-3, atol=1e-2)
+    # a synthetic crowd of confident priors (no forward): clamped count and sorted scores
+    Pn = eng.ctx.num_priors(H, W)
+    g = torch.Generator().manual_seed(0)
+    preds = torch.randn(1, Pn, 16, generator=g) * 0.5
+    preds[..., 0] += 1.0
+    preds[..., 5] += 1.0
+    d2, c2, _ = eng.decode_nms(preds.cuda(), H, W, 0.3, 0.45, max_det=500)
+    assert 0 < int(c2[0]) <= 500
+    s_ = d2[0, :int(c2[0]), 4].cpu()
+    assert bool((s_[:-1] >= s_[1:]).all())

@@ -62,7 +62,18 @@ def test_train_step_through_autograd_and_torch_sgd(arch, seed):
     core = plugins._engine_for(m.backbone, m.neck, m.bbox_head).core
     assigned = core._bufs[('assigned', (B, 2100), torch.int32)].cpu().numpy()
     if not np.array_equal(assigned, g['assigned_gt_inds']):
-        pytest.skip('assignment differs from golden by cost ties only (checked elsewhere)')
+        # a cost tie resolved in another order than the golden run: the golden losses belong to the
+        # other order; the plugin path must then agree with the ENGINE path on the same inputs (whose
+        # value parity on tie-equivalent assignments is established in test_gpu_parity)
+        from libfacedetection.train_b200 import YuNetEngine
+        d = np.load(os.path.join(GOLDEN, f'weights_{arch}.npz'))
+        eng = YuNetEngine(arch)
+        eng.load_state_dict({k: torch.from_numpy(d[k]) for k in d.files})
+        gt, offs = synthetic.pack_gt_csr(gb, gk)
+        le = eng.train_step(img, torch.from_numpy(gt).cuda(), torch.from_numpy(offs).cuda(), step=False).cpu().numpy()
+        for i, k in enumerate(('loss_cls', 'loss_bbox', 'loss_obj', 'loss_kps')):
+            assert abs(out['log_vars'][k] - le[i]) <= 1e-5 * max(1.0, abs(le[i])), k
+        return
     ref_l = g['losses']
     for i, k in enumerate(('loss_cls', 'loss_bbox', 'loss_obj', 'loss_kps')):
         assert abs(out['log_vars'][k] - ref_l[i]) <= 1e-3 * max(1.0, abs(ref_l[i])), k
@@ -104,3 +115,34 @@ def test_engine_export_round_trip(arch):
     text = eng.export_cpp()
     assert hashlib.sha256(text.encode()).hexdigest() == gold['sha256']
     assert len(eng.export_onnx(320, 320)) > 100000
+
+
+@pytest.mark.parametrize('seed', [0, 1, 2])
+def test_assigner_assign_matches_oracle(seed):
+    """``SimOTAAssigner.assign`` (the per-image entry the reference head calls,
+    sim_ota_assigner.py:38-93 / yunet_head.py:575-577) through ``yunet_simota_assign_ext``:
+    index-exact ``gt_inds``, matched IoU and labels against the oracle on the same inputs."""
+    from oracle import yunet_oracle as orc
+    m = _model('yunet_n').eval()
+    size = 320
+    img = torch.from_numpy(synthetic.make_images(1, size, seed)).cuda()
+    gb, gl, gk = synthetic.make_gt(1, size, seed)
+    cls, bbox, obj, kps = m.feature_test(img)
+    fl = lambda lst: torch.cat([t.permute(0, 2, 3, 1).reshape(1, -1, t.shape[1]) for t in lst], 1)[0]  # noqa: E731
+    cls_p, bbox_p, obj_p = fl(cls).cpu(), fl(bbox).cpu(), fl(obj).cpu()[:, 0]
+    priors = torch.cat(orc.grid_priors([(size // s, size // s) for s in (8, 16, 32)], (8, 16, 32)))
+    decoded = orc.bbox_decode(priors, bbox_p)
+    offset_priors = torch.cat([priors[:, :2] + priors[:, 2:] * 0.5, priors[:, 2:]], -1)
+    scores = cls_p.sigmoid() * obj_p.unsqueeze(1).sigmoid()
+    gtb, gtl = torch.from_numpy(gb[0]), torch.from_numpy(gl[0])
+    ref_inds, ref_ov = orc.simota_assign(scores, offset_priors, decoded, gtb, gtl)
+    asg = plugins.SimOTAAssigner(center_radius=2.5, candidate_topk=10, iou_weight=3.0, cls_weight=1.0)
+    res = asg.assign(scores.cuda(), offset_priors.cuda(), decoded.cuda(), gtb.cuda(), gtl.cuda())
+    assert res.num_gts == gtb.shape[0] and res.num_preds == 2100
+    assert torch.equal(res.gt_inds.cpu(), ref_inds), int((res.gt_inds.cpu() != ref_inds).sum())
+    assert _rel(res.max_overlaps, ref_ov) < 1e-5
+    pos = ref_inds > 0
+    assert torch.equal(res.labels.cpu()[pos], gtl[ref_inds[pos] - 1].long()) and bool((res.labels.cpu()[~pos] == -1).all())
+    # no ground truth -> everything background, zero overlaps (sim_ota_assigner.py:137-151)
+    empty = asg.assign(scores.cuda(), offset_priors.cuda(), decoded.cuda(), gtb[:0].cuda(), gtl[:0].cuda())
+    assert int(empty.gt_inds.abs().sum()) == 0 and float(empty.max_overlaps.abs().sum()) == 0.0

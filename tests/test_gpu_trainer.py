@@ -1,0 +1,105 @@
+"""GPU tests of the rows SURVEY 8(f) marks next: the training loop (N1: LR schedule + engine,
+checkpoint round trip bit-exact, CUDA-graph replay identical to eager launches) and the WIDER
+test-time driver on the engine (N4: variable-shape inputs, modes 0 / 1 / 2)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+from libfacedetection.train_b200 import YuNetEngine, evaluation, synthetic, trainer  # noqa: E402
+from oracle import yunet_oracle as orc  # noqa: E402
+
+
+def _batches(B, size, n, seed0=0):
+    out = []
+    for i in range(n):
+        img = torch.from_numpy(synthetic.make_images(B, size, seed0 + i)).cuda()
+        gb, gl, gk = synthetic.make_gt(B, size, seed0 + i)
+        gt, offs = synthetic.pack_gt_csr(gb, gk)
+        out.append((img, torch.from_numpy(gt).cuda(), torch.from_numpy(offs).cuda()))
+    return out
+
+
+def test_training_lowers_the_loss_and_checkpoints_round_trip(tmp_path):
+    """30 iterations of ``trainer.train`` (reference LR schedule, SGD 0.9 / 5e-4) on a fixed
+    synthetic set lower the total loss; save -> load into a fresh engine -> the next step is
+    bit-identical (parameters, momentum, BN running statistics all restored)."""
+    B, size = 16, 320
+    eng = YuNetEngine('yunet_n')
+    eng.init_weights(0)
+    data = _batches(B, size, 4)
+    logs = []
+    # the un-normalised 0..255 inputs need the reference's warm-up start (0.001 x lr): base_lr scaled
+    it = trainer.train(eng, data * 8, epochs=1, iters_per_epoch=30, base_lr=0.01, log_every=1,
+                       log=logs.append)
+    assert it == 30 and len(logs) == 30
+    first = np.mean([float(l.rsplit(' ', 1)[1]) for l in logs[:4]])
+    last = np.mean([float(l.rsplit(' ', 1)[1]) for l in logs[-4:]])
+    print(f'loss {first:.3f} -> {last:.3f}')
+    assert np.isfinite(last) and last < first
+    path = str(tmp_path / 'ck.pth')
+    trainer.save_checkpoint(eng, path, epoch=0, iteration=it)
+    eng2 = YuNetEngine('yunet_n')
+    meta = trainer.load_checkpoint(eng2, path)
+    assert meta['iter'] == 30
+    assert torch.equal(eng.params, eng2.params) and torch.equal(eng.momentum_buf, eng2.momentum_buf)
+    assert torch.equal(eng.bn_running, eng2.bn_running)
+    lr = trainer.lr_at(it, 0)
+    l1 = eng.train_step(*data[1], lr=lr).clone()
+    l2 = eng2.train_step(*data[1], lr=lr).clone()
+    assert torch.equal(l1, l2) and torch.equal(eng.params, eng2.params)
+    # the file is a reference-format checkpoint: strict-loads into the oracle's parameter set
+    sd = torch.load(path, weights_only=False)['state_dict']
+    P, Bf = orc.split_state_dict(sd)
+    d = np.load(os.path.join(GOLDEN, 'weights_yunet_n.npz'))
+    assert list(sd.keys()) == list(d.files)
+
+
+def test_cuda_graph_step_is_bit_identical_to_eager_launches():
+    """``train_step_graph`` (capture once, replay; lr as a device scalar) against ``train_step`` on
+    twin engines over 8 iterations of the warm-up schedule with two alternating input slots."""
+    B, size = 8, 320
+    a, b = YuNetEngine('yunet_n'), YuNetEngine('yunet_n')
+    a.init_weights(1)
+    b.init_weights(1)
+    data = _batches(B, size, 2, seed0=5)
+    for it in range(8):
+        lr = trainer.lr_at(it + 700, 0)
+        la = a.train_step(*data[it % 2], lr=lr).clone()
+        lb = b.train_step_graph(*data[it % 2], lr=lr).clone()
+        assert torch.equal(la, lb), (it, la, lb)
+    assert torch.equal(a.params, b.params) and torch.equal(a.momentum_buf, b.momentum_buf)
+    assert torch.equal(a.bn_running, b.bn_running)
+    assert sum(1 for v in b._graphs.values() if v != 'seen') == 2      # one graph per input slot
+
+
+def test_wider_test_driver_on_the_engine_all_modes():
+    """``evaluation.engine_detector`` + ``prepare_test_image`` on variable-shape images, modes 0
+    (640 box), 2 (origin size, padded to x32) and 1 (1100 x 1650 box): detections equal the oracle's
+    ``get_bboxes`` on the same prepared image, rescaled by the same factor."""
+    eng = YuNetEngine('yunet_n')
+    d = np.load(os.path.join(GOLDEN, 'weights_yunet_n.npz'))
+    sd = {k: torch.from_numpy(d[k]) for k in d.files}
+    eng.load_state_dict(sd)
+    P, Bf = orc.split_state_dict(sd)
+    detect = evaluation.engine_detector(eng, 0.02, 0.45)
+    rng = np.random.default_rng(0)
+    shapes = [(480, 640), (333, 517), (768, 1024)]
+    for mode in (0, 2, 1):
+        for (h, w) in shapes[:2 if mode == 1 else 3]:
+            img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+            chw, factor = evaluation.prepare_test_image(img, mode)
+            assert chw.shape[1] % 32 == 0 and chw.shape[2] % 32 == 0
+            mine = detect(chw, factor)
+            with torch.no_grad():
+                outs = orc.model_forward(torch.from_numpy(chw)[None], P, Bf, 'yunet_n', training=False)
+                ref = orc.get_bboxes(*outs, scale_factors=[factor])[0][0].numpy()
+            assert mine.shape[0] == ref.shape[0], (mode, h, w, mine.shape, ref.shape)
+            if ref.shape[0]:
+                key = lambda a: a[np.lexsort((a[:, 1], a[:, 0]))]      # noqa: E731
+                np.testing.assert_allclose(key(mine), key(ref.reshape(-1, 5)), rtol=1e-3, atol=1e-2)

@@ -77,3 +77,36 @@ def test_cpu_parameters_are_refused():
     m = plugins.DETECTORS.build(model_cfg('yunet_s'))
     with pytest.raises(RuntimeError):
         m.feature_test(torch.zeros(1, 3, 64, 64))
+
+
+@pytest.mark.reference
+def test_register_into_mmdet_builds_the_plugins_from_the_reference_config():
+    """With the reference's own registries (imported from /root/reference through the mmcv stub of
+    oracle/ref_loader.py): after ``register_into_mmdet()`` the real ``configs/yunet_n.py`` model
+    dict builds the plugin classes — the reference's ``build_detector`` call site needs no change —
+    and the assigner the head config names resolves to the plugin with an ``assign`` method."""
+    from oracle import ref_loader
+    if not ref_loader.reference_available():
+        pytest.skip('/root/reference not present')
+    ref_loader.install()
+    from mmdet.models.builder import MODELS, build_detector
+    from mmdet.core.bbox.builder import BBOX_ASSIGNERS as MM_ASSIGNERS, build_assigner
+    saved = {k: MODELS.get(k) for k in ('YuNetBackbone', 'TFPN', 'YuNet_Head', 'YuNet')}
+    saved_a = MM_ASSIGNERS.get('SimOTAAssigner')
+    try:
+        plugins.register_into_mmdet(force=True)
+        cfg = ref_loader.load_config('yunet_n')
+        det = build_detector(cfg.model)
+        assert type(det) is plugins.YuNet
+        assert type(det.backbone) is plugins.YuNetBackbone and type(det.neck) is plugins.TFPN
+        assert type(det.bbox_head) is plugins.YuNet_Head
+        import torch
+        sd = torch.load('/root/reference/weights/yunet_n.pth', map_location='cpu', weights_only=False)['state_dict']
+        det.load_state_dict(sd, strict=True)          # "All keys matched"
+        asg = build_assigner(cfg.model.train_cfg.assigner)
+        assert type(asg) is plugins.SimOTAAssigner and callable(asg.assign)
+        assert asg.center_radius == 2.5 and asg.candidate_topk == 10
+    finally:
+        for k, v in saved.items():
+            MODELS.register_module(name=k, force=True, module=v)
+        MM_ASSIGNERS.register_module(name='SimOTAAssigner', force=True, module=saved_a)
