@@ -27,6 +27,7 @@ struct yunet_ctx {
   long long launches = 0;       // kernels launched by this ctx (bench.py's gpu_launches)
   int opt_tc_forward = 1;       // use the tcgen05 unit kernel where it applies (default on)
   int opt_tc_backward = 1;      // same for the unit backward (64->64 plain units)
+  int opt_st_backward = 1;      // strip-streaming tcgen05 unit backward (unit_bwd_st.cu) where it applies
   int opt_ws_forward = 1;       // warp-specialised streaming unit kernel (unit_fwd_ws.cu) where it applies
   bool profiling = false;
   std::vector<ProfEvent> prof;
@@ -496,10 +497,14 @@ int yunet_backward(yunet_ctx* ctx, const float* img, const float* params, const 
       double bytes = 4.0 * B * (2.0 * u.cin * hw * (u.mode == LOAD_POOL ? 4.0 : 1.0) +
                                 (u.has_bn ? 2.0 : 1.0) * u.cout * hw);
       if (u.mode == LOAD_UPADD) bytes += 4.0 * B * 2.0 * u.cin * hw / 4.0;
-      const bool tc = ctx->opt_tc_backward && unit_bwd_tc_supported(u.cin, u.cout, u.mode, a.has_bn);
-      Scope sc(ctx, s, (tc ? "bwd_tc:" : "bwd:") + u.name, bytes);
-      e = tc ? launch_unit_bwd_tc(u.mode, a, ctx->num_sms, v.status() + 1, s)
-             : launch_unit_bwd(u.cin, u.cout, u.mode, a, ctx->num_sms, s);
+      // st_backward: 0 off, 1 where it is the faster kernel (default), 2 wherever it applies (tests)
+      const bool st = ctx->opt_st_backward && unit_bwd_st_supported(u.cin, u.cout, u.mode, a.has_bn, a.H, a.W) &&
+                      (ctx->opt_st_backward >= 2 || unit_bwd_st_preferred(u.mode, a.H, a.W));
+      const bool tc = !st && ctx->opt_tc_backward && unit_bwd_tc_supported(u.cin, u.cout, u.mode, a.has_bn);
+      Scope sc(ctx, s, (st ? "bwd_st:" : tc ? "bwd_tc:" : "bwd:") + u.name, bytes);
+      e = st ? launch_unit_bwd_st(u.mode, a, ctx->num_sms, v.status() + 1, s)
+          : tc ? launch_unit_bwd_tc(u.mode, a, ctx->num_sms, v.status() + 1, s)
+               : launch_unit_bwd(u.cin, u.cout, u.mode, a, ctx->num_sms, s);
     }
     if (e != cudaSuccess) return fail(ctx, (int)e, "backward: unit %s: %s", u.name.c_str(), cudaGetErrorString(e));
   }
@@ -579,6 +584,7 @@ int yunet_set_option(yunet_ctx* ctx, const char* name, int value) {
   if (strcmp(name, "tc_forward") == 0) { ctx->opt_tc_forward = value ? 1 : 0; return 0; }
   if (strcmp(name, "tc_backward") == 0) { ctx->opt_tc_backward = value ? 1 : 0; return 0; }
   if (strcmp(name, "ws_forward") == 0) { ctx->opt_ws_forward = value ? 1 : 0; return 0; }
+  if (strcmp(name, "st_backward") == 0) { ctx->opt_st_backward = value < 0 ? 0 : (value > 2 ? 2 : value); return 0; }
   return fail(ctx, -1, "unknown option %s", name);
 }
 

@@ -126,6 +126,11 @@ int unit_bwd_tc_supported(int cin, int cout, int mode, int has_bn);
 cudaError_t launch_unit_bwd_tc(int mode, const UnitBwdArgs& a, int num_sms, int* status,
                                cudaStream_t s);
 
+// ---- unit_bwd_st.cu: the tcgen05 backward on strips (register-window depthwise stage, 94 % tile use) ----
+int unit_bwd_st_supported(int cin, int cout, int mode, int has_bn, int H, int W);
+int unit_bwd_st_preferred(int mode, int H, int W);   // shapes where it beats the per-tile kernel
+cudaError_t launch_unit_bwd_st(int mode, const UnitBwdArgs& a, int num_sms, int* status, cudaStream_t s);
+
 // ---- launchers (kernels_bwd.cu) ----
 cudaError_t launch_unit_bwd(int cin, int cout, int mode, const UnitBwdArgs& a, int num_sms,
                             cudaStream_t s);

@@ -75,10 +75,12 @@ def test_tc_forward_matches_reference_golden():
 
 
 @pytest.mark.parametrize('arch', ['yunet_n', 'yunet_s'])
-@pytest.mark.parametrize('shape', [(3, 96, 160), (2, 320, 320)])
-def test_tc_backward_equals_fp32_path(arch, shape):
-    """Same forward, same upstream gradient: parameter gradients of the tcgen05 backward kernel vs
-    the exact-fp32 CUDA-core backward (identical ReLU/pool decisions by construction)."""
+@pytest.mark.parametrize('shape', [(3, 96, 160), (2, 320, 320), (2, 640, 320)])
+@pytest.mark.parametrize('path', ['tc', 'st'])
+def test_tc_backward_equals_fp32_path(arch, shape, path):
+    """Same forward, same upstream gradient: parameter gradients of the tcgen05 backward kernels
+    (`tc`: per-tile unit_bwd_tc.cu, `st`: strip-streaming unit_bwd_st.cu) vs the exact-fp32
+    CUDA-core backward (identical ReLU/pool decisions by construction)."""
     B, H, W = shape
     eng = _engine(arch)
     rng = np.random.default_rng(33)
@@ -86,8 +88,10 @@ def test_tc_backward_equals_fp32_path(arch, shape):
     preds = eng.forward(img, train=True)
     d_preds = torch.from_numpy(rng.standard_normal(tuple(preds.shape)).astype(np.float32)).cuda()
     eng.set_option('tc_backward', 0)
+    eng.set_option('st_backward', 0)
     g0 = eng.backward(img, d_preds).clone()
     eng.set_option('tc_backward', 1)
+    eng.set_option('st_backward', 2 if path == 'st' else 0)      # 2: the strip kernel wherever it applies
     g1 = eng.backward(img, d_preds).clone()
     torch.cuda.synchronize()
     flags = eng.status_flags(B, H, W, True)
@@ -101,4 +105,4 @@ def test_tc_backward_equals_fp32_path(arch, shape):
         err = float((a - b).abs().max())
         worst = max(worst, err / (scale + 1e-4 * gmax))
         assert err <= 1e-4 * scale + 1e-5 * gmax, (name, err, scale)
-    print(f'{arch} {shape}: tc backward vs fp32 backward, worst normalised grad err {worst:.3e}')
+    print(f'{arch} {shape} {path}: tc backward vs fp32 backward, worst normalised grad err {worst:.3e}')
