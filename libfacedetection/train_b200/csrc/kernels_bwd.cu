@@ -596,7 +596,11 @@ __global__ void __launch_bounds__(NT, (CIN * COUT <= 1024) ? 2 : 1) unit_bwd_ker
 // d(conv1.weight)[co][c][ky][kx] = sum_p g[p][co] * img[c][2y+ky-1][2x+kx-1],  d(bias) = sum_p g
 constexpr int ST_TH = 8, ST_TW = 32;
 constexpr int ST_IH = 2 * ST_TH + 1, ST_IW = 2 * ST_TW + 1;
-constexpr int ST_IWP = ST_IW + 2;
+// the patch is staged as aligned float4 columns -4 .. 2*ST_TW-1 around the tile's first input column
+// (17 per row; input column x of the patch sits at float index x + 3)
+constexpr int ST_C4 = 2 * ST_TW / 4 + 1;
+constexpr int ST_IWP = ST_C4 * 4;
+constexpr int ST_NPG = 28;       // pixel groups of the weight-gradient GEMM (9 threads each)
 
 // L2 prefetch of the next stem tile: image rows (3 planes, 128-byte lines) and, for the backward,
 // the du / z_out rows of the 16-channel output tile
@@ -629,8 +633,12 @@ __device__ __forceinline__ void stem_prefetch_next(const float* img, const float
   }
 }
 
-__global__ void __launch_bounds__(256, 3) stem_bwd_kernel(const StemBwdArgs a) {
-  __shared__ float sIn[3][ST_IH][ST_IWP];
+// Thread mapping of the GEMM  dW[co][c,ky,kx] += g[p][co] * in[c][2y+ky-1][2x+kx-1]:
+//   thread = (c,ky) x pixel group, 16 co x 3 kx accumulators in registers; per pixel 4 broadcast
+//   LDS.128 of g + 3 LDS of the input row feed 24 packed FMAs (the previous 4 x 3 tile issued an
+//   index computation and 4 loads per 12 FMAs and was issue-bound at 73 warp instructions / pixel).
+__global__ void __launch_bounds__(256, 2) stem_bwd_kernel(const StemBwdArgs a) {
+  __shared__ __align__(16) float sIn[3][ST_IH][ST_IWP];
   __shared__ __align__(16) float sGs[ST_TH * ST_TW][16];
   __shared__ float sCo[5][16];
   const int tid = threadIdx.x;
@@ -644,17 +652,19 @@ __global__ void __launch_bounds__(256, 3) stem_bwd_kernel(const StemBwdArgs a) {
     sCo[4][tid] = k.rstd;
   }
   __syncthreads();
-  // thread -> (co quad, (c,ky) row of 3 taps), pixel group
-  const int o = tid % 36;
-  const int grp = tid / 36;            // 0..6 (tid >= 252: idle in the GEMM)
-  const int coq = o / 9, ck = o % 9;   // ck = c*3 + ky
-  const int c = ck / 3, ky = ck % 3;
-  float acc[4][3];
+  const int ck = tid % 9, pg = tid / 9;         // ck = c*3 + ky; pg 0..27 (tid >= 252 idle in the GEMM)
+  const int c = ck / 3, ky = ck - c * 3;
+  float acc[16][3];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 16; ++i)
 #pragma unroll
     for (int j = 0; j < 3; ++j) acc[i][j] = 0.f;
-  float bsum = 0.f;   // bias gradient partial of channel tid & 15
+  // BN-backward constants of this thread's channel quad (tid & 3 is the quad of every g item it stages)
+  const int q = tid & 3;
+  float4 k_gs, k_m1, k_m2, k_mu, k_rs;
+  k_gs = lds4(&sCo[0][q * 4]); k_m1 = lds4(&sCo[1][q * 4]); k_m2 = lds4(&sCo[2][q * 4]);
+  k_mu = lds4(&sCo[3][q * 4]); k_rs = lds4(&sCo[4][q * 4]);
+  float4 bsum = f4(0.f);                        // bias gradient partial of channels 4q .. 4q+3
 
   const int tiles_x = (Wo + ST_TW - 1) / ST_TW, tiles_y = (Ho + ST_TH - 1) / ST_TH;
   const int ntiles = tiles_x * tiles_y * a.B;
@@ -664,53 +674,52 @@ __global__ void __launch_bounds__(256, 3) stem_bwd_kernel(const StemBwdArgs a) {
     const int ty = t % tiles_y;
     const int b = t / tiles_y;
     const int ox0 = tx * ST_TW, oy0 = ty * ST_TH;
-    const int ix0 = 2 * ox0 - 1, iy0 = 2 * oy0 - 1;
+    const int iy0 = 2 * oy0 - 1;
     stem_prefetch_next(a.img, a.du, a.zout, a.B, a.Hin, a.Win, tile + gridDim.x, ntiles, tiles_x,
                        tiles_y, tid);
-#pragma unroll 4
-    for (int i = tid; i < 3 * ST_IH * ST_IW; i += 256) {
-      int cc = i / (ST_IH * ST_IW);
-      int r = (i / ST_IW) % ST_IH;
-      int x = i % ST_IW;
-      int gy = iy0 + r, gx = ix0 + x;
-      float v = 0.f;
+    for (int i = tid; i < 3 * ST_IH * ST_C4; i += 256) {
+      const int rowid = i / ST_C4, j = i - rowid * ST_C4;
+      const int cc = rowid / ST_IH, r = rowid - cc * ST_IH;
+      const int gy = iy0 + r, gx = 2 * ox0 - 4 + 4 * j;       // Win % 4 == 0: a chunk is all in or all out
+      float4 v = f4(0.f);
       if (gy >= 0 && gy < a.Hin && gx >= 0 && gx < a.Win)
-        v = __ldg(a.img + (((long long)b * 3 + cc) * a.Hin + gy) * a.Win + gx);
-      sIn[cc][r][x] = v;
+        v = ldg4(a.img + (((long long)b * 3 + cc) * a.Hin + gy) * a.Win + gx);
+      sts4(&sIn[cc][r][4 * j], v);
     }
 #pragma unroll
     for (int it = 0; it < ST_TH * ST_TW * 4 / 256; ++it) {
-      const int i = tid + it * 256;
-      const int pix = i / 4, q = i % 4;
+      const int pix = (tid >> 2) + it * 64;
       const int oy = oy0 + pix / ST_TW, ox = ox0 + pix % ST_TW;
       float4 g = f4(0.f);
       if (oy < Ho && ox < Wo) {
         const long long off = (((long long)b * Ho + oy) * Wo + ox) * 16 + q * 4;
         const float4 d = ldg4(a.du + off), z = ldg4(a.zout + off);
-        g.x = sCo[0][q * 4 + 0] * (d.x - sCo[1][q * 4 + 0] - (z.x - sCo[3][q * 4 + 0]) * sCo[4][q * 4 + 0] * sCo[2][q * 4 + 0]);
-        g.y = sCo[0][q * 4 + 1] * (d.y - sCo[1][q * 4 + 1] - (z.y - sCo[3][q * 4 + 1]) * sCo[4][q * 4 + 1] * sCo[2][q * 4 + 1]);
-        g.z = sCo[0][q * 4 + 2] * (d.z - sCo[1][q * 4 + 2] - (z.z - sCo[3][q * 4 + 2]) * sCo[4][q * 4 + 2] * sCo[2][q * 4 + 2]);
-        g.w = sCo[0][q * 4 + 3] * (d.w - sCo[1][q * 4 + 3] - (z.w - sCo[3][q * 4 + 3]) * sCo[4][q * 4 + 3] * sCo[2][q * 4 + 3]);
+        g.x = k_gs.x * (d.x - k_m1.x - (z.x - k_mu.x) * k_rs.x * k_m2.x);
+        g.y = k_gs.y * (d.y - k_m1.y - (z.y - k_mu.y) * k_rs.y * k_m2.y);
+        g.z = k_gs.z * (d.z - k_m1.z - (z.z - k_mu.z) * k_rs.z * k_m2.z);
+        g.w = k_gs.w * (d.w - k_m1.w - (z.w - k_mu.w) * k_rs.w * k_m2.w);
       }
+      bsum = add4(bsum, g);
       sts4(&sGs[pix][q * 4], g);
     }
     __syncthreads();
-    if (tid < 252) {
-      for (int p = grp; p < ST_TH * ST_TW; p += 7) {
-        const int ly = p / ST_TW, lx = p % ST_TW;
-        const float4 g = lds4(&sGs[p][coq * 4]);
-        const float* row = &sIn[c][2 * ly + ky][2 * lx];
+    if (tid < 9 * ST_NPG) {
+#pragma unroll 2
+      for (int p = pg; p < ST_TH * ST_TW; p += ST_NPG) {
+        const int ly = p / ST_TW, lx = p - ly * ST_TW;
+        const float* row = &sIn[c][2 * ly + ky][2 * lx + 3];
         const float v0 = row[0], v1 = row[1], v2 = row[2];
-        acc[0][0] = fmaf(g.x, v0, acc[0][0]); acc[0][1] = fmaf(g.x, v1, acc[0][1]); acc[0][2] = fmaf(g.x, v2, acc[0][2]);
-        acc[1][0] = fmaf(g.y, v0, acc[1][0]); acc[1][1] = fmaf(g.y, v1, acc[1][1]); acc[1][2] = fmaf(g.y, v2, acc[1][2]);
-        acc[2][0] = fmaf(g.z, v0, acc[2][0]); acc[2][1] = fmaf(g.z, v1, acc[2][1]); acc[2][2] = fmaf(g.z, v2, acc[2][2]);
-        acc[3][0] = fmaf(g.w, v0, acc[3][0]); acc[3][1] = fmaf(g.w, v1, acc[3][1]); acc[3][2] = fmaf(g.w, v2, acc[3][2]);
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 g = lds4(&sGs[p][j4 * 4]);
+          fma2(acc[j4 * 4 + 0][0], acc[j4 * 4 + 1][0], g.x, g.y, v0, v0);
+          fma2(acc[j4 * 4 + 2][0], acc[j4 * 4 + 3][0], g.z, g.w, v0, v0);
+          fma2(acc[j4 * 4 + 0][1], acc[j4 * 4 + 1][1], g.x, g.y, v1, v1);
+          fma2(acc[j4 * 4 + 2][1], acc[j4 * 4 + 3][1], g.z, g.w, v1, v1);
+          fma2(acc[j4 * 4 + 0][2], acc[j4 * 4 + 1][2], g.x, g.y, v2, v2);
+          fma2(acc[j4 * 4 + 2][2], acc[j4 * 4 + 3][2], g.z, g.w, v2, v2);
+        }
       }
-    }
-    {
-      const int bc = tid & 15;
-#pragma unroll 4
-      for (int p = tid >> 4; p < ST_TH * ST_TW; p += 16) bsum += sGs[p][bc];
     }
     __syncthreads();
   }
@@ -719,14 +728,16 @@ __global__ void __launch_bounds__(256, 3) stem_bwd_kernel(const StemBwdArgs a) {
   __syncthreads();
   for (int i = tid; i < 448; i += 256) sRed[i] = 0.f;
   __syncthreads();
-  if (tid < 252) {
+  if (tid < 9 * ST_NPG) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 16; ++i)
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx)
-        atomicAdd(sRed + (coq * 4 + i) * 27 + c * 9 + ky * 3 + kx, acc[i][kx]);
+      for (int kx = 0; kx < 3; ++kx) atomicAdd(sRed + i * 27 + c * 9 + ky * 3 + kx, acc[i][kx]);
   }
-  atomicAdd(sRed + 432 + (tid & 15), bsum);
+  atomicAdd(sRed + 432 + q * 4 + 0, bsum.x);
+  atomicAdd(sRed + 432 + q * 4 + 1, bsum.y);
+  atomicAdd(sRed + 432 + q * 4 + 2, bsum.z);
+  atomicAdd(sRed + 432 + q * 4 + 3, bsum.w);
   __syncthreads();
   float* dst = a.partial + (long long)blockIdx.x * kPartialStride;
   for (int i = tid; i < 448; i += 256) dst[i] = sRed[i];
@@ -807,9 +818,10 @@ cudaError_t launch_unit_bwd(int cin, int cout, int mode, const UnitBwdArgs& a, i
 }
 
 cudaError_t launch_stem_bwd(const StemBwdArgs& a, int num_sms, cudaStream_t s) {
+  if (a.Win & 3) return cudaErrorInvalidValue;     // float4 staging of the image rows
   const int Ho = a.Hin / 2, Wo = a.Win / 2;
   const int ntiles = ((Wo + ST_TW - 1) / ST_TW) * ((Ho + ST_TH - 1) / ST_TH) * a.B;
-  int grid = 3 * num_sms < ntiles ? 3 * num_sms : ntiles;
+  int grid = 2 * num_sms < ntiles ? 2 * num_sms : ntiles;
   if (grid > kMaxPartialCtas) grid = kMaxPartialCtas;
   stem_bwd_kernel<<<grid, 256, 0, s>>>(a);
   cudaError_t e = cudaGetLastError();

@@ -334,10 +334,13 @@ __global__ void __launch_bounds__(NT, 2) unit_fwd_kernel(const UnitFwdArgs a) {
 // so every broadcast weight load feeds two pixels; per-lane fp64 statistics across tiles.
 constexpr int ST_TH = 16, ST_TW = 32;
 constexpr int ST_IH = 2 * ST_TH + 1, ST_IW = 2 * ST_TW + 1;   // 33 x 65 input patch
-constexpr int ST_IWP = ST_IW + 2;                             // row stride 67
+// the patch is staged as aligned float4 columns -4 .. 2*ST_TW-1 around the tile's first input column
+// (17 per row; input column x of the patch sits at float index x + 3)
+constexpr int ST_C4 = 2 * ST_TW / 4 + 1;
+constexpr int ST_IWP = ST_C4 * 4;                             // row stride 68
 
 __global__ void __launch_bounds__(256, 2) stem_fwd_kernel(const StemArgs a) {
-  __shared__ float sIn[3][ST_IH][ST_IWP];
+  __shared__ __align__(16) float sIn[3][ST_IH][ST_IWP];
   __shared__ __align__(16) float sW[27][16];
   __shared__ float sB[16];
   __shared__ double sRedD[8][32];
@@ -359,7 +362,7 @@ __global__ void __launch_bounds__(256, 2) stem_fwd_kernel(const StemArgs a) {
     const int ty = t % tiles_y;
     const int b = t / tiles_y;
     const int ox0 = tx * ST_TW, oy0 = ty * ST_TH;
-    const int ix0 = 2 * ox0 - 1, iy0 = 2 * oy0 - 1;
+    const int iy0 = 2 * oy0 - 1;
     {   // L2 prefetch of the next tile's image rows (3 planes, 128-byte lines)
       const int nt = tile + gridDim.x;
       if (nt < ntiles) {
@@ -380,16 +383,14 @@ __global__ void __launch_bounds__(256, 2) stem_fwd_kernel(const StemArgs a) {
       }
     }
     __syncthreads();      // previous tile's readers of sIn are done (also covers the weight setup)
-#pragma unroll 4
-    for (int i = tid; i < 3 * ST_IH * ST_IW; i += 256) {
-      int c = i / (ST_IH * ST_IW);
-      int r = (i / ST_IW) % ST_IH;
-      int x = i % ST_IW;
-      int gy = iy0 + r, gx = ix0 + x;
-      float v = 0.f;
+    for (int i = tid; i < 3 * ST_IH * ST_C4; i += 256) {
+      const int rowid = i / ST_C4, j = i - rowid * ST_C4;
+      const int c = rowid / ST_IH, r = rowid - c * ST_IH;
+      const int gy = iy0 + r, gx = 2 * ox0 - 4 + 4 * j;       // Win % 4 == 0: a chunk is all in or all out
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (gy >= 0 && gy < a.Hin && gx >= 0 && gx < a.Win)
-        v = __ldg(a.img + (((long long)b * 3 + c) * a.Hin + gy) * a.Win + gx);
-      sIn[c][r][x] = v;
+        v = __ldg(reinterpret_cast<const float4*>(a.img + (((long long)b * 3 + c) * a.Hin + gy) * a.Win + gx));
+      *reinterpret_cast<float4*>(&sIn[c][r][4 * j]) = v;
     }
     __syncthreads();
 
@@ -402,8 +403,8 @@ __global__ void __launch_bounds__(256, 2) stem_fwd_kernel(const StemArgs a) {
       for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
-          const float v0 = sIn[c][2 * ly + ky][2 * lx + kx];
-          const float v1 = sIn[c][2 * (ly + 8) + ky][2 * lx + kx];
+          const float v0 = sIn[c][2 * ly + ky][2 * lx + kx + 3];
+          const float v1 = sIn[c][2 * (ly + 8) + ky][2 * lx + kx + 3];
           const int k = c * 9 + ky * 3 + kx;
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
@@ -559,6 +560,7 @@ cudaError_t launch_unit_fwd(int cin, int cout, int mode, const UnitFwdArgs& a, i
 }
 
 cudaError_t launch_stem_fwd(const StemArgs& a, int num_sms, cudaStream_t s) {
+  if (a.Win & 3) return cudaErrorInvalidValue;     // float4 staging of the image rows
   const int Ho = a.Hin / 2, Wo = a.Win / 2;
   const int tiles = ((Wo + ST_TW - 1) / ST_TW) * ((Ho + ST_TH - 1) / ST_TH) * a.B;
   int grid = 2 * num_sms;
