@@ -81,7 +81,7 @@ def test_cuda_graph_step_matches_eager_launches():
     # weights against the 0..255 input mean) are round-off residue that the momentum integrates
     # (measured: 1.3e-5 on a parameter after 8 steps, eager vs eager and eager vs graph alike)
     assert float((a.params - b.params).abs().max()) < 1e-4
-    assert torch.allclose(a.bn_running, b.bn_running, rtol=2e-3, atol=1e-5)
+    assert torch.allclose(a.bn_running, b.bn_running, rtol=1e-3, atol=1e-3)     # statistics of 0..255-scale activations
     assert sum(1 for v in b._graphs.values() if v != 'seen') == 2      # one graph per input slot
 
 
