@@ -17,6 +17,7 @@
 // Parameter gradients are accumulated in registers across all tiles of a CTA and flushed with one
 // round of atomics at the end.
 #include <cstdio>
+#include <cstdlib>
 
 #include "kernels.h"
 #include "prefetch.cuh"
@@ -108,8 +109,8 @@ struct BwdCfg {
   static_assert(TP % NPG1 == 0 && TP % NPG2 == 0, "gemm mapping");
 };
 
-template <int CIN, int COUT, int MODE, int HAS_BN>
-__global__ void __launch_bounds__(NT, (CIN * COUT <= 1024) ? 2 : 1) unit_bwd_kernel(const UnitBwdArgs a) {
+template <int CIN, int COUT, int MODE, int HAS_BN, int OCC>
+__global__ void __launch_bounds__(NT, OCC) unit_bwd_kernel(const UnitBwdArgs a) {
   using C = BwdCfg<CIN, COUT>;
   extern __shared__ float4 smem_raw[];
   float* smem = reinterpret_cast<float*>(smem_raw);
@@ -602,44 +603,17 @@ constexpr int ST_C4 = 2 * ST_TW / 4 + 1;
 constexpr int ST_IWP = ST_C4 * 4;
 constexpr int ST_NPG = 28;       // pixel groups of the weight-gradient GEMM (9 threads each)
 
-// L2 prefetch of the next stem tile: image rows (3 planes, 128-byte lines) and, for the backward,
-// the du / z_out rows of the 16-channel output tile
-__device__ __forceinline__ void stem_prefetch_next(const float* img, const float* du, const float* zout,
-                                                   int B, int Hin, int Win, int nt, int ntiles,
-                                                   int tiles_x, int tiles_y, int tid) {
-  if (nt >= ntiles) return;
-  int t2 = nt;
-  const int ntx = t2 % tiles_x; t2 /= tiles_x;
-  const int nty = t2 % tiles_y;
-  const int nb = t2 / tiles_y;
-  const int ox0 = ntx * ST_TW, oy0 = nty * ST_TH;
-  const int ix0 = 2 * ox0 - 1, iy0 = 2 * oy0 - 1;
-  constexpr int LPR = (ST_IW * 4 + 127) / 128 + 1;       // 128-byte lines per input row (unaligned)
-  for (int i = tid; i < 3 * ST_IH * LPR; i += 256) {
-    const int c = i / (ST_IH * LPR), r = (i / LPR) % ST_IH, l = i % LPR;
-    const int gy = iy0 + r;
-    int gx = ix0 + l * 32;
-    if (gx < 0) gx = 0;
-    if (gy >= 0 && gy < Hin && gx < Win && gx < ix0 + ST_IW)
-      l2_prefetch_line(img + (((long long)nb * 3 + c) * Hin + gy) * Win + gx);
-  }
-  if (du != nullptr) {
-    const int Ho = Hin / 2, Wo = Win / 2;
-    const int which = tid >> 5, r = tid & 31;
-    if (which == 6)
-      l2_prefetch_tile<16>(du + (long long)nb * Ho * Wo * 16, Ho, Wo, oy0, oy0 + ST_TH, ox0, ox0 + ST_TW, r);
-    if (which == 7)
-      l2_prefetch_tile<16>(zout + (long long)nb * Ho * Wo * 16, Ho, Wo, oy0, oy0 + ST_TH, ox0, ox0 + ST_TW, r);
-  }
-}
-
 // Thread mapping of the GEMM  dW[co][c,ky,kx] += g[p][co] * in[c][2y+ky-1][2x+kx-1]:
 //   thread = (c,ky) x pixel group, 16 co x 3 kx accumulators in registers; per pixel 4 broadcast
 //   LDS.128 of g + 3 LDS of the input row feed 24 packed FMAs (the previous 4 x 3 tile issued an
 //   index computation and 4 loads per 12 FMAs and was issue-bound at 73 warp instructions / pixel).
+// Double buffered: the next tile's image patch and raw du / z_out rows are copied in with cp.async
+// while the current tile is reduced (the staging loads were ~28 % of the stall samples).
+constexpr int ST_PATCH = 3 * ST_IH * ST_IWP;                 // floats
+constexpr int ST_BUF = ST_PATCH + 2 * ST_TH * ST_TW * 16;    // + du tile (-> g in place) + z_out tile
+
 __global__ void __launch_bounds__(256, 2) stem_bwd_kernel(const StemBwdArgs a) {
-  __shared__ __align__(16) float sIn[3][ST_IH][ST_IWP];
-  __shared__ __align__(16) float sGs[ST_TH * ST_TW][16];
+  extern __shared__ __align__(16) float stem_smem[];
   __shared__ float sCo[5][16];
   const int tid = threadIdx.x;
   const int Ho = a.Hin / 2, Wo = a.Win / 2;
@@ -668,50 +642,74 @@ __global__ void __launch_bounds__(256, 2) stem_bwd_kernel(const StemBwdArgs a) {
 
   const int tiles_x = (Wo + ST_TW - 1) / ST_TW, tiles_y = (Ho + ST_TH - 1) / ST_TH;
   const int ntiles = tiles_x * tiles_y * a.B;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  auto stage = [&](int tile, int buf) {
     int t = tile;
     const int tx = t % tiles_x; t /= tiles_x;
     const int ty = t % tiles_y;
     const int b = t / tiles_y;
     const int ox0 = tx * ST_TW, oy0 = ty * ST_TH;
-    const int iy0 = 2 * oy0 - 1;
-    stem_prefetch_next(a.img, a.du, a.zout, a.B, a.Hin, a.Win, tile + gridDim.x, ntiles, tiles_x,
-                       tiles_y, tid);
+    const int gx0 = 2 * ox0 - 4, iy0 = 2 * oy0 - 1;
+    float* dst = stem_smem + buf * ST_BUF;
     for (int i = tid; i < 3 * ST_IH * ST_C4; i += 256) {
       const int rowid = i / ST_C4, j = i - rowid * ST_C4;
       const int cc = rowid / ST_IH, r = rowid - cc * ST_IH;
-      const int gy = iy0 + r, gx = 2 * ox0 - 4 + 4 * j;       // Win % 4 == 0: a chunk is all in or all out
-      float4 v = f4(0.f);
-      if (gy >= 0 && gy < a.Hin && gx >= 0 && gx < a.Win)
-        v = ldg4(a.img + (((long long)b * 3 + cc) * a.Hin + gy) * a.Win + gx);
-      sts4(&sIn[cc][r][4 * j], v);
+      const int gy = iy0 + r, gx = gx0 + 4 * j;            // Win % 4 == 0: a chunk is all in or all out
+      const bool in = gy >= 0 && gy < a.Hin && gx >= 0 && gx < a.Win;
+      const float* src = in ? a.img + (((long long)b * 3 + cc) * a.Hin + gy) * a.Win + gx : a.img;
+      cp_async16(dst + rowid * ST_IWP + 4 * j, src, in);
     }
+    // du / z_out: item (pixel, quad) -> the thread that later turns it into g (no barrier in between)
+#pragma unroll
+    for (int it = 0; it < ST_TH * ST_TW * 4 / 256; ++it) {
+      const int pix = (tid >> 2) + it * 64;
+      const int oy = oy0 + pix / ST_TW, ox = ox0 + pix % ST_TW;
+      const bool in = oy < Ho && ox < Wo;
+      const long long off = in ? (((long long)b * Ho + oy) * Wo + ox) * 16 + q * 4 : 0;
+      cp_async16(dst + ST_PATCH + pix * 16 + q * 4, a.du + off, in);
+      cp_async16(dst + ST_PATCH + ST_TH * ST_TW * 16 + pix * 16 + q * 4, a.zout + off, in);
+    }
+  };
+  if ((int)blockIdx.x < ntiles) stage(blockIdx.x, 0);
+  cp_async_commit();
+
+  int buf = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
+    int t = tile;
+    const int tx = t % tiles_x; t /= tiles_x;
+    const int ty = t % tiles_y;
+    const int ox0 = tx * ST_TW, oy0 = ty * ST_TH;
+    __syncthreads();      // the GEMM readers of the other buffer (previous tile) are done
+    if (tile + (int)gridDim.x < ntiles) stage(tile + gridDim.x, buf ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();   // this tile's copies (all but the group just committed) have landed
+    float* sIn = stem_smem + buf * ST_BUF;                     // [3][ST_IH][ST_IWP]
+    float* sGs = sIn + ST_PATCH;                               // [pixels][16]: du -> g in place
+    const float* sZ = sGs + ST_TH * ST_TW * 16;
 #pragma unroll
     for (int it = 0; it < ST_TH * ST_TW * 4 / 256; ++it) {
       const int pix = (tid >> 2) + it * 64;
       const int oy = oy0 + pix / ST_TW, ox = ox0 + pix % ST_TW;
       float4 g = f4(0.f);
       if (oy < Ho && ox < Wo) {
-        const long long off = (((long long)b * Ho + oy) * Wo + ox) * 16 + q * 4;
-        const float4 d = ldg4(a.du + off), z = ldg4(a.zout + off);
+        const float4 d = lds4(sGs + pix * 16 + q * 4), z = lds4(sZ + pix * 16 + q * 4);
         g.x = k_gs.x * (d.x - k_m1.x - (z.x - k_mu.x) * k_rs.x * k_m2.x);
         g.y = k_gs.y * (d.y - k_m1.y - (z.y - k_mu.y) * k_rs.y * k_m2.y);
         g.z = k_gs.z * (d.z - k_m1.z - (z.z - k_mu.z) * k_rs.z * k_m2.z);
         g.w = k_gs.w * (d.w - k_m1.w - (z.w - k_mu.w) * k_rs.w * k_m2.w);
       }
       bsum = add4(bsum, g);
-      sts4(&sGs[pix][q * 4], g);
+      sts4(sGs + pix * 16 + q * 4, g);
     }
     __syncthreads();
     if (tid < 9 * ST_NPG) {
 #pragma unroll 2
       for (int p = pg; p < ST_TH * ST_TW; p += ST_NPG) {
         const int ly = p / ST_TW, lx = p - ly * ST_TW;
-        const float* row = &sIn[c][2 * ly + ky][2 * lx + 3];
+        const float* row = sIn + (c * ST_IH + 2 * ly + ky) * ST_IWP + 2 * lx + 3;
         const float v0 = row[0], v1 = row[1], v2 = row[2];
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4) {
-          const float4 g = lds4(&sGs[p][j4 * 4]);
+          const float4 g = lds4(sGs + p * 16 + j4 * 4);
           fma2(acc[j4 * 4 + 0][0], acc[j4 * 4 + 1][0], g.x, g.y, v0, v0);
           fma2(acc[j4 * 4 + 2][0], acc[j4 * 4 + 3][0], g.z, g.w, v0, v0);
           fma2(acc[j4 * 4 + 0][1], acc[j4 * 4 + 1][1], g.x, g.y, v1, v1);
@@ -721,10 +719,10 @@ __global__ void __launch_bounds__(256, 2) stem_bwd_kernel(const StemBwdArgs a) {
         }
       }
     }
-    __syncthreads();
   }
+  cp_async_wait<0>();
   // flush: shared-memory reduction, one partial vector [gw (432) | gb (16)] per CTA
-  float* sRed = &sGs[0][0];
+  float* sRed = stem_smem;
   __syncthreads();
   for (int i = tid; i < 448; i += 256) sRed[i] = 0.f;
   __syncthreads();
@@ -767,11 +765,11 @@ __global__ void bn_param_grads_kernel(const BnFinalizeArgs a, const double* dsum
   grad[a.beta_off[i] + c] = (float)dsum[a.ch_off[i] + c];
 }
 
-template <int CIN, int COUT, int MODE, int HAS_BN>
-cudaError_t launch_unit_bwd_t(const UnitBwdArgs& a, int num_sms, cudaStream_t s) {
+template <int CIN, int COUT, int MODE, int HAS_BN, int OCC>
+cudaError_t launch_unit_bwd_o(const UnitBwdArgs& a, int num_sms, cudaStream_t s) {
   using C = BwdCfg<CIN, COUT>;
   const size_t smem = sizeof(float) * C::SMEM_FLOATS;
-  auto kern = unit_bwd_kernel<CIN, COUT, MODE, HAS_BN>;
+  auto kern = unit_bwd_kernel<CIN, COUT, MODE, HAS_BN, OCC>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -779,7 +777,7 @@ cudaError_t launch_unit_bwd_t(const UnitBwdArgs& a, int num_sms, cudaStream_t s)
     configured = true;
   }
   const int ntiles = ((a.W + C::TW - 1) / C::TW) * ((a.H + C::TH - 1) / C::TH) * a.B;
-  const int per_sm = (CIN * COUT <= 1024) ? 2 : 1;
+  const int per_sm = OCC;
   int grid = per_sm * num_sms < ntiles ? per_sm * num_sms : ntiles;
   if (grid > kMaxPartialCtas) grid = kMaxPartialCtas;
   kern<<<grid, NT, smem, s>>>(a);
@@ -787,6 +785,19 @@ cudaError_t launch_unit_bwd_t(const UnitBwdArgs& a, int num_sms, cudaStream_t s)
   if (e != cudaSuccess) return e;
   // gw1, gb1, gw2, gb2 are adjacent in the bucket in this order (plan.cpp)
   return launch_reduce_partials(a.partial, grid, COUT * CIN + 11 * COUT, a.gw1, s);
+}
+
+// CTAs per SM: two for the small-weight units (128 registers, the persistent gradient accumulators
+// spill ~400 B) -- YUNET_BWD_OCC=1 selects the spill-free single-CTA build of the 16-channel units
+// (development knob, read once)
+template <int CIN, int COUT, int MODE, int HAS_BN>
+cudaError_t launch_unit_bwd_t(const UnitBwdArgs& a, int num_sms, cudaStream_t s) {
+  constexpr int DEF = (CIN * COUT <= 1024) ? 2 : 1;
+  if (CIN == 16 && DEF == 2) {
+    static const int occ = [] { const char* e = getenv("YUNET_BWD_OCC"); return e ? atoi(e) : 0; }();
+    if (occ == 1) return launch_unit_bwd_o<CIN, COUT, MODE, HAS_BN, (CIN == 16 ? 1 : DEF)>(a, num_sms, s);
+  }
+  return launch_unit_bwd_o<CIN, COUT, MODE, HAS_BN, DEF>(a, num_sms, s);
 }
 
 template <int CIN, int COUT>
@@ -823,7 +834,14 @@ cudaError_t launch_stem_bwd(const StemBwdArgs& a, int num_sms, cudaStream_t s) {
   const int ntiles = ((Wo + ST_TW - 1) / ST_TW) * ((Ho + ST_TH - 1) / ST_TH) * a.B;
   int grid = 2 * num_sms < ntiles ? 2 * num_sms : ntiles;
   if (grid > kMaxPartialCtas) grid = kMaxPartialCtas;
-  stem_bwd_kernel<<<grid, 256, 0, s>>>(a);
+  const int smem = 2 * ST_BUF * (int)sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e0 = cudaFuncSetAttribute(stem_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e0 != cudaSuccess) return e0;
+    configured = true;
+  }
+  stem_bwd_kernel<<<grid, 256, smem, s>>>(a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   return launch_reduce_partials(a.partial, grid, 448, a.gw, s);   // [weight (432) | bias (16)]

@@ -340,7 +340,11 @@ constexpr int ST_C4 = 2 * ST_TW / 4 + 1;
 constexpr int ST_IWP = ST_C4 * 4;                             // row stride 68
 
 __global__ void __launch_bounds__(256, 2) stem_fwd_kernel(const StemArgs a) {
-  __shared__ __align__(16) float sIn[3][ST_IH][ST_IWP];
+  // two patch buffers: the next tile is copied in (cp.async, zero-filled outside the image) while
+  // the current one is convolved -- the staging loads were 25 % of the stall samples (long scoreboard)
+  extern __shared__ __align__(16) float stem_smem[];
+  typedef float Patch[3][ST_IH][ST_IWP];
+  Patch* sInB = reinterpret_cast<Patch*>(stem_smem);
   __shared__ __align__(16) float sW[27][16];
   __shared__ float sB[16];
   __shared__ double sRedD[8][32];
@@ -356,43 +360,38 @@ __global__ void __launch_bounds__(256, 2) stem_fwd_kernel(const StemArgs a) {
   const int lx = tid % ST_TW, ly = tid / ST_TW;    // ly in 0..7; second pixel at ly + 8
   double stat = 0.0;    // lane L: sum of channel L (L < 16) / sum of squares of channel L-16
 
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  auto stage = [&](int tile, int buf) {
+    int t = tile;
+    const int tx = t % tiles_x; t /= tiles_x;
+    const int ty = t % tiles_y;
+    const int b = t / tiles_y;
+    const int gx0 = 2 * tx * ST_TW - 4, iy0 = 2 * ty * ST_TH - 1;
+    float* dst = &sInB[buf][0][0][0];
+    for (int i = tid; i < 3 * ST_IH * ST_C4; i += 256) {
+      const int rowid = i / ST_C4, j = i - rowid * ST_C4;
+      const int c = rowid / ST_IH, r = rowid - c * ST_IH;
+      const int gy = iy0 + r, gx = gx0 + 4 * j;            // Win % 4 == 0: a chunk is all in or all out
+      const bool in = gy >= 0 && gy < a.Hin && gx >= 0 && gx < a.Win;
+      const float* src = in ? a.img + (((long long)b * 3 + c) * a.Hin + gy) * a.Win + gx : a.img;
+      cp_async16(dst + rowid * ST_IWP + 4 * j, src, in);
+    }
+  };
+  if ((int)blockIdx.x < ntiles) stage(blockIdx.x, 0);
+  cp_async_commit();
+
+  int buf = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
     int t = tile;
     const int tx = t % tiles_x; t /= tiles_x;
     const int ty = t % tiles_y;
     const int b = t / tiles_y;
     const int ox0 = tx * ST_TW, oy0 = ty * ST_TH;
-    const int iy0 = 2 * oy0 - 1;
-    {   // L2 prefetch of the next tile's image rows (3 planes, 128-byte lines)
-      const int nt = tile + gridDim.x;
-      if (nt < ntiles) {
-        int t2 = nt;
-        const int ntx = t2 % tiles_x; t2 /= tiles_x;
-        const int nty = t2 % tiles_y;
-        const int nb = t2 / tiles_y;
-        const int nix0 = 2 * ntx * ST_TW - 1, niy0 = 2 * nty * ST_TH - 1;
-        constexpr int LPR = (ST_IW * 4 + 127) / 128 + 1;
-        for (int i = tid; i < 3 * ST_IH * LPR; i += 256) {
-          const int c = i / (ST_IH * LPR), r = (i / LPR) % ST_IH, l = i % LPR;
-          const int gy = niy0 + r;
-          int gx = nix0 + l * 32;
-          if (gx < 0) gx = 0;
-          if (gy >= 0 && gy < a.Hin && gx < a.Win && gx < nix0 + ST_IW)
-            l2_prefetch_line(a.img + (((long long)nb * 3 + c) * a.Hin + gy) * a.Win + gx);
-        }
-      }
-    }
-    __syncthreads();      // previous tile's readers of sIn are done (also covers the weight setup)
-    for (int i = tid; i < 3 * ST_IH * ST_C4; i += 256) {
-      const int rowid = i / ST_C4, j = i - rowid * ST_C4;
-      const int c = rowid / ST_IH, r = rowid - c * ST_IH;
-      const int gy = iy0 + r, gx = 2 * ox0 - 4 + 4 * j;       // Win % 4 == 0: a chunk is all in or all out
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (gy >= 0 && gy < a.Hin && gx >= 0 && gx < a.Win)
-        v = __ldg(reinterpret_cast<const float4*>(a.img + (((long long)b * 3 + c) * a.Hin + gy) * a.Win + gx));
-      *reinterpret_cast<float4*>(&sIn[c][r][4 * j]) = v;
-    }
+    __syncthreads();      // the readers of the other buffer (previous tile) are done; covers the weight setup
+    if (tile + (int)gridDim.x < ntiles) stage(tile + gridDim.x, buf ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();   // everything but the group just committed: this tile's patch has landed
     __syncthreads();
+    const Patch& sIn = sInB[buf];
 
     float acc[2][16];
 #pragma unroll
@@ -565,7 +564,14 @@ cudaError_t launch_stem_fwd(const StemArgs& a, int num_sms, cudaStream_t s) {
   const int tiles = ((Wo + ST_TW - 1) / ST_TW) * ((Ho + ST_TH - 1) / ST_TH) * a.B;
   int grid = 2 * num_sms;
   if (grid > tiles) grid = tiles;
-  stem_fwd_kernel<<<grid, 256, 0, s>>>(a);
+  const int smem = 2 * 3 * ST_IH * ST_IWP * (int)sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(stem_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  stem_fwd_kernel<<<grid, 256, smem, s>>>(a);
   return cudaGetLastError();
 }
 

@@ -28,4 +28,18 @@ __device__ __forceinline__ void l2_prefetch_tile(const float* img, int H, int W,
     l2_prefetch_bulk(img + ((long long)y * W + x_lo) * C, (uint32_t)((x_hi - x_lo) * C * 4));
 }
 
+// 16-byte asynchronous global -> shared copy (LDGSTS); `valid == false` writes 16 zero bytes (the
+// source address must still be a mapped one).  Double-buffered staging of the next tile by the
+// persistent CUDA-core kernels: commit one group per tile, wait_group<1> before consuming.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  const int n = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 }  // namespace yunet

@@ -20,7 +20,16 @@ KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'smsp__issue_active.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum',
         'sm__cycles_elapsed.max', 'launch__registers_per_thread', 'launch__grid_size',
         'launch__block_size', 'launch__shared_mem_per_block_dynamic',
-        'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum']
+        'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum',
+        'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',
+        'l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum', 'l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum',
+        'l1tex__t_requests_pipe_lsu_mem_global_op_st.sum', 'l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum',
+        'l1tex__t_sectors_pipe_lsu_mem_local_op_ld.sum', 'l1tex__t_sectors_pipe_lsu_mem_local_op_st.sum',
+        'lts__t_sectors_op_write.sum', 'lts__t_sectors_op_read.sum',
+        'sm__inst_executed_pipe_lsu.sum', 'sm__inst_executed_pipe_fma.sum', 'sm__inst_executed_pipe_alu.sum',
+        'sm__inst_executed_pipe_fmaheavy.sum', 'sm__inst_executed_pipe_fp64.sum',
+        'sm__warps_active.avg.per_cycle_active', 'launch__occupancy_limit_registers',
+        'launch__occupancy_limit_shared_mem', 'launch__waves_per_multiprocessor']
 
 
 def short(name):
