@@ -296,19 +296,41 @@ def plugin_e2e(arch, B, S, dev, steps, warmup):
     bb_all, kp_all = torch.cat(hb).pin_memory(), torch.cat(hk).pin_memory()
     lb_all = torch.cat(hl).pin_memory()
     counts = [int(x.shape[0]) for x in hb]
-    dimg = torch.empty_like(himg, device=dev)
+    # a prefetching loader: the next batch is uploaded on a copy stream while this one trains
+    dimgs = [torch.empty_like(himg, device=dev) for _ in range(2)]
+    copy_stream, main = torch.cuda.Stream(device=dev), torch.cuda.current_stream()
+    ready = [torch.cuda.Event() for _ in range(2)]
+    freed = [torch.cuda.Event() for _ in range(2)]
+    staged = [None, None]
+
+    def upload(slot):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(freed[slot])
+            dimgs[slot].copy_(himg, non_blocking=True)
+            flat = [t.to(dev, non_blocking=True) for t in (bb_all, kp_all, lb_all)]
+            for t in flat:
+                t.record_stream(main)          # allocated on the copy stream, consumed on the main one
+            staged[slot] = tuple(t.split(counts) for t in flat)
+            ready[slot].record(copy_stream)
+
+    state = {'i': 0}
+    for ev in freed:
+        ev.record(main)
+    upload(0)
 
     def step():
-        dimg.copy_(himg, non_blocking=True)
-        db = bb_all.to(dev, non_blocking=True).split(counts)
-        dk = kp_all.to(dev, non_blocking=True).split(counts)
-        dl = lb_all.to(dev, non_blocking=True).split(counts)
-        data = dict(img=dimg, img_metas=[{}] * B, gt_bboxes=list(db), gt_labels=list(dl),
+        slot = state['i'] % 2
+        state['i'] += 1
+        upload(slot ^ 1)
+        main.wait_event(ready[slot])
+        db, dk, dl = staged[slot]
+        data = dict(img=dimgs[slot], img_metas=[{}] * B, gt_bboxes=list(db), gt_labels=list(dl),
                     gt_keypointss=list(dk))
         opt.zero_grad()
         out = m.train_step(data)              # log_vars: host floats (D2H of the four losses)
         out['loss'].backward()
         opt.step()
+        freed[slot].record(main)
         return out
 
     for _ in range(warmup):
@@ -322,7 +344,7 @@ def plugin_e2e(arch, B, S, dev, steps, warmup):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
     h2d = himg.numel() * 4 + bb_all.numel() * 4 + kp_all.numel() * 4 + lb_all.numel() * 8
-    del m, opt, dimg
+    del m, opt, dimgs, staged
     torch.cuda.empty_cache()
     return {'value': B / (ms / 1e3), 'unit': UNIT, 'ms_per_step': ms, 'steps': steps,
             'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 16,

@@ -124,6 +124,13 @@ __global__ void __launch_bounds__(NT, OCC) unit_bwd_kernel(const UnitBwdArgs a) 
   float* sCa = sB1 + COUT;                 // [4][CIN]  scale, shift, mean, rstd of input a
   float* sCb = sCa + 4 * CIN;              // [4][CIN]  ... of input b
   float* sCo = sCb + 4 * CIN;              // [5][COUT] gscale, m1, m2, mean, rstd of the output BN
+  // PF: the next tile's du / z_out halo rows are copied in with cp.async while this tile is in its
+  // GEMM / depthwise / epilogue phases (the staging loads were ~25 % of the stall samples); only where
+  // the extra buffers leave room for the CTAs per SM the kernel is built for
+  constexpr int RAWF = (HAS_BN ? 2 : 1) * C::HP * COUT;
+  constexpr bool PF = OCC == 2 && (C::SMEM_FLOATS + RAWF) * 4 <= 112 * 1024;
+  float* sRawD = sCo + 5 * COUT;           // [C::HP][COUT] raw du      (PF)
+  float* sRawZ = sRawD + C::HP * COUT;     // [C::HP][COUT] raw z_out   (PF, HAS_BN)
 
   const int tid = threadIdx.x;
   // ---- one-time setup
@@ -187,6 +194,30 @@ __global__ void __launch_bounds__(NT, OCC) unit_bwd_kernel(const UnitBwdArgs a) 
   const int ntiles = tiles_x * tiles_y * a.B;
   const long long in_img_stride = (MODE == 1) ? (long long)a.H * a.W * 4 * CIN : (long long)a.H * a.W * CIN;
 
+  auto stage_g = [&](int tile_) {
+    int t = tile_;
+    const int tx = t % tiles_x; t /= tiles_x;
+    const int ty = t % tiles_y;
+    const int b = t / tiles_y;
+    const int x0 = tx * C::TW, y0 = ty * C::TH;
+    constexpr int Q = COUT / 4;
+    const float* dimg = a.dout + (long long)b * a.dout_batch_stride;
+    const float* zimg = HAS_BN ? a.zout + (long long)b * a.H * a.W * COUT : nullptr;
+#pragma unroll 4
+    for (int it = 0; it < (C::HP * Q + NT - 1) / NT; ++it) {
+      const int i = tid + it * NT;
+      if (i >= C::HP * Q) break;
+      const int pix = i / Q, q = i % Q;
+      const int gy = y0 + pix / C::HW - 1, gx = x0 + pix % C::HW - 1;
+      const bool in = gy >= 0 && gy < a.H && gx >= 0 && gx < a.W;
+      const long long off = in ? ((long long)gy * a.W + gx) * COUT + q * 4 : 0;
+      cp_async16(sRawD + pix * COUT + q * 4, dimg + off, in);
+      if (HAS_BN) cp_async16(sRawZ + pix * COUT + q * 4, zimg + off, in);
+    }
+    cp_async_commit();
+  };
+  if (PF && (int)blockIdx.x < ntiles) stage_g(blockIdx.x);
+
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     int t = tile;
     const int tx = t % tiles_x; t /= tiles_x;
@@ -206,10 +237,11 @@ __global__ void __launch_bounds__(NT, OCC) unit_bwd_kernel(const UnitBwdArgs a) 
         const int nx0 = ntx * C::TW, ny0 = nty * C::TH;
         const int which = tid >> 6, r = tid & 63;
         if (which == 0) {
-          l2_prefetch_tile<COUT>(a.dout + (long long)nb * a.dout_batch_stride, a.H, a.W, ny0 - 1,
-                                 ny0 + C::TH + 1, nx0 - 1, nx0 + C::TW + 1, r);
+          if (!PF)
+            l2_prefetch_tile<COUT>(a.dout + (long long)nb * a.dout_batch_stride, a.H, a.W, ny0 - 1,
+                                   ny0 + C::TH + 1, nx0 - 1, nx0 + C::TW + 1, r);
         } else if (which == 1) {
-          if (HAS_BN)
+          if (HAS_BN && !PF)
             l2_prefetch_tile<COUT>(a.zout + (long long)nb * a.H * a.W * COUT, a.H, a.W, ny0 - 1,
                                    ny0 + C::TH + 1, nx0 - 1, nx0 + C::TW + 1, r);
         } else if (MODE == 1) {
@@ -230,6 +262,7 @@ __global__ void __launch_bounds__(NT, OCC) unit_bwd_kernel(const UnitBwdArgs a) 
       constexpr int Q = COUT / 4;
       const float* dimg = a.dout + (long long)b * a.dout_batch_stride;
       const float* zimg = HAS_BN ? a.zout + (long long)b * a.H * a.W * COUT : nullptr;
+      if (PF) cp_async_wait<0>();       // a thread reads back exactly the chunks it copied
 #pragma unroll 4
       for (int it = 0; it < (C::HP * Q + NT - 1) / NT; ++it) {
         const int i = tid + it * NT;
@@ -239,9 +272,9 @@ __global__ void __launch_bounds__(NT, OCC) unit_bwd_kernel(const UnitBwdArgs a) 
         float4 g = f4(0.f);
         if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) {
           const long long off = ((long long)gy * a.W + gx) * COUT + q * 4;
-          g = ldg4(dimg + off);
+          g = PF ? lds4(sRawD + pix * COUT + q * 4) : ldg4(dimg + off);
           if (HAS_BN) {
-            const float4 z = ldg4(zimg + off);
+            const float4 z = PF ? lds4(sRawZ + pix * COUT + q * 4) : ldg4(zimg + off);
             const float4 gs = lds4(sCo + 0 * COUT + q * 4), m1 = lds4(sCo + 1 * COUT + q * 4);
             const float4 m2 = lds4(sCo + 2 * COUT + q * 4), mu = lds4(sCo + 3 * COUT + q * 4);
             const float4 rs = lds4(sCo + 4 * COUT + q * 4);
@@ -290,6 +323,7 @@ __global__ void __launch_bounds__(NT, OCC) unit_bwd_kernel(const UnitBwdArgs a) 
       }
     }
     __syncthreads();
+    if (PF && tile + (int)gridDim.x < ntiles) stage_g(tile + gridDim.x);
 
     // ---- S1: GEMM1  y = a W1^T + b1  (zero for out-of-image pixels)
     {
@@ -768,7 +802,9 @@ __global__ void bn_param_grads_kernel(const BnFinalizeArgs a, const double* dsum
 template <int CIN, int COUT, int MODE, int HAS_BN, int OCC>
 cudaError_t launch_unit_bwd_o(const UnitBwdArgs& a, int num_sms, cudaStream_t s) {
   using C = BwdCfg<CIN, COUT>;
-  const size_t smem = sizeof(float) * C::SMEM_FLOATS;
+  constexpr int RAWF = (HAS_BN ? 2 : 1) * C::HP * COUT;
+  constexpr bool PF = OCC == 2 && (C::SMEM_FLOATS + RAWF) * 4 <= 112 * 1024;      // as in the kernel
+  const size_t smem = sizeof(float) * (C::SMEM_FLOATS + (PF ? RAWF : 0));
   auto kern = unit_bwd_kernel<CIN, COUT, MODE, HAS_BN, OCC>;
   static bool configured = false;
   if (!configured) {

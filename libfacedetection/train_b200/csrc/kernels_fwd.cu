@@ -101,6 +101,11 @@ __global__ void __launch_bounds__(NT, 2) unit_fwd_kernel(const UnitFwdArgs a) {
   float* sShA = sScA + CIN;
   float* sScB = sShA + CIN;
   float* sShB = sScB + CIN;
+  // PF (plain input, where it fits beside a second CTA): the next tile's raw halo rows are copied in
+  // with cp.async while this tile runs its GEMM / depthwise stages (the staging loads were ~40 % of
+  // the stall samples of the 160x160 16 -> 16 unit)
+  constexpr bool PF = MODE == 0 && (C::SMEM_FLOATS + C::HP * CIN) * 4 <= 112 * 1024;
+  float* sRaw = sShB + CIN;               // [C::HP][CIN] raw z of the next / current tile (PF)
 
   const int tid = threadIdx.x;
   const int tiles_x = (a.W + C::TW - 1) / C::TW;
@@ -136,6 +141,29 @@ __global__ void __launch_bounds__(NT, 2) unit_fwd_kernel(const UnitFwdArgs a) {
   const int dr0 = (tid / (C::NQ * C::TW)) * C::RPT;
   double st1[4] = {0.0, 0.0, 0.0, 0.0}, st2[4] = {0.0, 0.0, 0.0, 0.0};
 
+  auto stage_in = [&](int tile_) {
+    int t = tile_;
+    const int tx = t % tiles_x; t /= tiles_x;
+    const int ty = t % tiles_y;
+    const int b = t / tiles_y;
+    const int x0 = tx * C::TW, y0 = ty * C::TH;
+    constexpr int Q = CIN / 4;
+    const float* img = a.za + (long long)b * a.H * a.W * CIN;
+#pragma unroll 4
+    for (int it = 0; it < C::HPP * Q / NT; ++it) {
+      const int i = tid + it * NT;
+      const int pix = i / Q, q = i % Q;
+      if (pix < C::HP) {
+        const int hy = pix / C::HW, hx = pix % C::HW;
+        const int gy = y0 + hy - 1, gx = x0 + hx - 1;
+        const bool in = gy >= 0 && gy < a.H && gx >= 0 && gx < a.W;
+        cp_async16(sRaw + pix * CIN + q * 4, in ? img + ((long long)gy * a.W + gx) * CIN + q * 4 : a.za, in);
+      }
+    }
+    cp_async_commit();
+  };
+  if (PF && (int)blockIdx.x < ntiles) stage_in(blockIdx.x);
+
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
   int t = tile;
   const int tx = t % tiles_x; t /= tiles_x;
@@ -144,7 +172,7 @@ __global__ void __launch_bounds__(NT, 2) unit_fwd_kernel(const UnitFwdArgs a) {
   const int x0 = tx * C::TW, y0 = ty * C::TH;
 
   // ---- L2 prefetch of the next tile's input rows (one bulk request per row)
-  {
+  if (!PF) {
     const int nt = tile + gridDim.x;
     if (nt < ntiles && tid < 96) {
       int t2 = nt;
@@ -174,6 +202,7 @@ __global__ void __launch_bounds__(NT, 2) unit_fwd_kernel(const UnitFwdArgs a) {
     static_assert((C::HPP * Q) % NT == 0, "prologue trip count");
     // fixed trip count + partial unroll: the global loads of several iterations are in flight
     // together instead of one dependent load per iteration
+    if (PF) cp_async_wait<0>();         // a thread reads back exactly the chunks it copied
 #pragma unroll 4
     for (int it = 0; it < C::HPP * Q / NT; ++it) {
       const int i = tid + it * NT;
@@ -187,7 +216,7 @@ __global__ void __launch_bounds__(NT, 2) unit_fwd_kernel(const UnitFwdArgs a) {
           const float4 sh = *reinterpret_cast<const float4*>(sShA + q * 4);
           if (MODE == 0) {
             const float* p = a.za + (((long long)b * a.H + gy) * a.W + gx) * CIN + q * 4;
-            v = bn_relu4(ldg4(p), sc, sh);
+            v = bn_relu4(PF ? *reinterpret_cast<const float4*>(sRaw + pix * CIN + q * 4) : ldg4(p), sc, sh);
           } else if (MODE == 1) {
             const int W2 = a.W * 2;
             const float* p = a.za + (((long long)b * (a.H * 2) + gy * 2) * W2 + gx * 2) * CIN + q * 4;
@@ -211,6 +240,7 @@ __global__ void __launch_bounds__(NT, 2) unit_fwd_kernel(const UnitFwdArgs a) {
     }
   }
   __syncthreads();
+  if (PF && tile + (int)gridDim.x < ntiles) stage_in(tile + gridDim.x);
 
   // ---- stage 2: pointwise GEMM  y[p][co] = sum_ci a[p][ci] * W1[co][ci]
   const int cg = tid % C::NCG;
@@ -514,7 +544,8 @@ __global__ void grid_priors_kernel(float* priors, int h0, int w0, int s0, int h1
 template <int CIN, int COUT, int MODE>
 cudaError_t launch_unit_fwd_t(const UnitFwdArgs& a, int num_sms, cudaStream_t s) {
   using C = FwdCfg<CIN, COUT>;
-  const size_t smem = sizeof(float) * C::SMEM_FLOATS;
+  constexpr bool PF = MODE == 0 && (C::SMEM_FLOATS + C::HP * CIN) * 4 <= 112 * 1024;      // as in the kernel
+  const size_t smem = sizeof(float) * (C::SMEM_FLOATS + (PF ? C::HP * CIN : 0));
   auto kern = unit_fwd_kernel<CIN, COUT, MODE>;
   static bool configured = false;
   if (!configured) {

@@ -312,13 +312,28 @@ unit_bwd_st_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
 
     // ---- T0: stage the operand (MODE 1/2, real blocks); turn the prefetched du / z_out tiles into g
     const float* za_img = a.za + (long long)b * a.H * a.W * C64 * (MODE == 1 ? 4 : 1);
+    if (MODE != 0 && nx.valid && warp == 2) {
+      // the operand of the NEXT real block is read with plain loads at its T0: pull its rows into L2 now
+      const int nblk = nx.prime ? nx.blk + 1 : nx.blk;
+      const int ny0 = nblk * RB, nx0 = nx.sx * SW;
+      if (MODE == 1) {
+        l2_prefetch_tile<C64>(a.za + (long long)nx.b * a.H * a.W * C64 * 4, a.H * 2, a.W * 2, ny0 * 2,
+                              (ny0 + RB) * 2, (nx0 - 1) * 2, (nx0 - 1 + SWH) * 2, lane);
+      } else {
+        l2_prefetch_tile<C64>(a.za + (long long)nx.b * a.H * a.W * C64, a.H, a.W, ny0, ny0 + RB, nx0 - 1,
+                              nx0 - 1 + SWH, lane);
+        l2_prefetch_tile<C64>(a.zb + (long long)nx.b * (a.H >> 1) * (a.W >> 1) * C64, a.H >> 1, a.W >> 1,
+                              ny0 >> 1, ((ny0 + RB - 1) >> 1) + 1, (nx0 - 1) >> 1, ((nx0 + SWH - 2) >> 1) + 1,
+                              lane - 8);
+      }
+    }
     if (MODE != 0 && !st.prime) {
       // pooled / up-added operand a: vector loads (latency overlaps the waits on du / z_out)
+      int py = 0, px = tid >> 4;          // tile pixel (tid >> 4) + 16 k without a division
 #pragma unroll 4
-      for (int k = 0; k < 128 * 16 / NT; ++k) {
-        const int i = tid + k * NT;
-        const int pix = i >> 4, ch = i & 15;
-        const int py = pix / SWH, px = pix - py * SWH;
+      for (int k = 0; k < 128 * 16 / NT; ++k, px += 16) {
+        while (px >= SWH) { px -= SWH; ++py; }
+        const int pix = (tid >> 4) + 16 * k, ch = tid & 15;
         const int gy = y0 + py, gx = x0 - 1 + px;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (py < RB && gy < a.H && gx >= 0 && gx < a.W) {
@@ -357,11 +372,11 @@ unit_bwd_st_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     if (alive) {
       // g = gamma*rstd*(du - mean(du) - zhat*mean(du*zhat)) in place; the g tile holds image rows
       // y0+1 .. y0+RB (one row below the block's own rows), exact 0 outside the image
+      int py = 0, px = tid >> 4;          // tile pixel (tid >> 4) + 16 k without a division
 #pragma unroll 4
-      for (int k = 0; k < 128 * 16 / NT; ++k) {
-        const int i = tid + k * NT;
-        const int pix = i >> 4, ch = i & 15;
-        const int py = pix / SWH, px = pix - py * SWH;
+      for (int k = 0; k < 128 * 16 / NT; ++k, px += 16) {
+        while (px >= SWH) { px -= SWH; ++py; }
+        const int pix = (tid >> 4) + 16 * k, ch = tid & 15;
         const int gy = y0 + 1 + py, gx = x0 - 1 + px;
         float* gp = const_cast<float*>(rchunk(sG, pix, ch));
         float4 g = make_float4(0.f, 0.f, 0.f, 0.f);

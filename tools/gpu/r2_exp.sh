@@ -1,7 +1,7 @@
 #!/bin/bash
 # experiments: default build, then the development knobs, one short bench each
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_tc.py -m gpu -q -x -p no:cacheprovider > gpurun_out/pytest_exp.log 2>&1; tail -3 gpurun_out/pytest_exp.log
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_tc.py tests/test_gpu_plugins.py -m gpu -q -x -p no:cacheprovider > gpurun_out/pytest_exp.log 2>&1; tail -3 gpurun_out/pytest_exp.log
 run() { tag=$1; shift; env "$@" timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-extra --kernel-table gpurun_out/k_$tag.json > gpurun_out/bench_$tag.log 2>&1
   python - "$tag" <<'P'
 import json, sys
@@ -9,11 +9,10 @@ tag = sys.argv[1]
 try:
     d = json.loads(open(f'gpurun_out/bench_{tag}.log').read().strip().splitlines()[-1])
     k = json.load(open(f'gpurun_out/k_{tag}.json'))
-    print(tag, 'ms/step', round(d['ms_per_step'], 3), 'eager', round(d['cuda_graph']['eager_ms_per_step'], 3))
-    print('   ', ' | '.join('%s %.3f' % (r['kernel'].replace('backbone.', ''), r['ms']) for r in k[:14]))
+    print(tag, 'ms/step', round(d['ms_per_step'], 3), 'eager', round(d['cuda_graph']['eager_ms_per_step'], 3), 'e2e', round(d['e2e']['ms_per_step'], 3))
+    print('   ', ' | '.join('%s %.3f' % (r['kernel'].replace('backbone.', ''), r['ms']) for r in k[:16]))
 except Exception as e:
     print(tag, 'failed', e); print(open(f'gpurun_out/bench_{tag}.log').read()[-600:])
 P
 }
 run default A=1
-run occ1 YUNET_BWD_OCC=1
