@@ -25,6 +25,10 @@ namespace {
 
 constexpr int NT = 256;
 constexpr int NW = NT / 32;
+// the assignment runs one CTA per image and its time is that of the image with the most faces (one warp
+// per gt in phase 2): 16 warps halve the rounds of the crowded images, two CTAs still fit an SM
+constexpr int NTA = 512;
+constexpr int NWA = NTA / 32;
 constexpr int KTOP = 10;   // per-lane candidate list length (candidate_topk <= 10)
 constexpr int GT_ROW = 19;
 constexpr int PC = 16;     // prediction channels
@@ -117,7 +121,7 @@ __device__ __forceinline__ void decode_box(const float* pr, float px, float py, 
 struct AssignExt { const float* scores; const float* priors; const float* boxes; };
 
 template <bool EXT>
-__global__ void __launch_bounds__(NT) simota_assign_kernel(
+__global__ void __launch_bounds__(NTA) simota_assign_kernel(
     const yunet_loss_cfg_dev lc, const LevelGeom geo, const float* __restrict__ preds,
     const float* __restrict__ gt, const int* __restrict__ gt_offsets, int* __restrict__ assigned,
     float* __restrict__ matched_iou, float* counters, Cand* gscratch, int vcap, const AssignExt ext) {
@@ -135,10 +139,10 @@ __global__ void __launch_bounds__(NT) simota_assign_kernel(
   extern __shared__ float4 smem_raw[];
   Cand* scand = reinterpret_cast<Cand*>(smem_raw);                       // [vcap]
   unsigned char* sflag = reinterpret_cast<unsigned char*>(scand + vcap); // [P]
-  __shared__ int s_warp[NW];
+  __shared__ int s_warp[NWA];
   __shared__ int s_base;
   __shared__ int s_V;
-  __shared__ float s_red[2][NW];
+  __shared__ float s_red[2][NWA];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x;
@@ -152,7 +156,7 @@ __global__ void __launch_bounds__(NT) simota_assign_kernel(
 
   // ---- pass A: validity flag per prior, zero the outputs
   int nvalid_local = 0;
-  for (int p = tid; p < P; p += NT) {
+  for (int p = tid; p < P; p += NTA) {
     float ox, oy, s;
     offset_prior(p, ox, oy, s);
     bool any_gt = false, any_ct = false;
@@ -176,7 +180,7 @@ __global__ void __launch_bounds__(NT) simota_assign_kernel(
     __syncthreads();
     if (tid == 0) {
       int t = 0;
-      for (int w = 0; w < NW; ++w) t += s_warp[w];
+      for (int w = 0; w < NWA; ++w) t += s_warp[w];
       s_V = t;
       s_base = 0;
     }
@@ -187,7 +191,7 @@ __global__ void __launch_bounds__(NT) simota_assign_kernel(
   Cand* cand = (V <= vcap) ? scand : (gscratch + (long long)b * P);
 
   // ---- pass B: ordered compaction + per-candidate decode and classification cost
-  for (int base = 0; base < P; base += NT) {
+  for (int base = 0; base < P; base += NTA) {
     const int p = base + tid;
     const bool v = p < P && sflag[p] != 0;
     const unsigned m = __ballot_sync(0xffffffffu, v);
@@ -222,7 +226,7 @@ __global__ void __launch_bounds__(NT) simota_assign_kernel(
     __syncthreads();
     if (tid == 0) {
       int t = 0;
-      for (int w = 0; w < NW; ++w) t += s_warp[w];
+      for (int w = 0; w < NWA; ++w) t += s_warp[w];
       s_base += t;
     }
     __syncthreads();
@@ -230,7 +234,7 @@ __global__ void __launch_bounds__(NT) simota_assign_kernel(
 
   // ---- phase 2: one warp per gt: dynamic k from the top-k IoUs, then the k cheapest candidates
   const int K = lc.candidate_topk < KTOP ? lc.candidate_topk : KTOP;
-  for (int g = warp; g < G; g += NW) {
+  for (int g = warp; g < G; g += NWA) {
     const float4 gb = load_gt_box(gtb, g);
     float ti[KTOP];
     unsigned long long kc[KTOP];
@@ -300,7 +304,7 @@ __global__ void __launch_bounds__(NT) simota_assign_kernel(
   // ---- phase 3: resolve multi-matched priors (argmin over ALL gts, sim_ota_assigner.py:244-249),
   // matched IoU, outputs, counters
   float npos = 0.f, wsum = 0.f;
-  for (int v = tid; v < V; v += NT) {
+  for (int v = tid; v < V; v += NTA) {
     const Cand c = cand[v];
     if (c.cnt == 0) continue;
     int gsel = c.gsel;
@@ -333,7 +337,7 @@ __global__ void __launch_bounds__(NT) simota_assign_kernel(
   __syncthreads();
   if (tid == 0) {
     float a = 0.f, c = 0.f;
-    for (int w = 0; w < NW; ++w) { a += s_red[0][w]; c += s_red[1][w]; }
+    for (int w = 0; w < NWA; ++w) { a += s_red[0][w]; c += s_red[1][w]; }
     atomicAdd(counters + 0, a);
     atomicAdd(counters + 1, c);
   }
@@ -494,7 +498,7 @@ cudaError_t launch_simota_assign(const yunet_loss_cfg_dev& lc, const LevelGeom& 
     if (e != cudaSuccess) return e;
     configured = smem;
   }
-  simota_assign_kernel<false><<<B, NT, smem, s>>>(lc, g, preds, gt, gt_offsets, assigned, matched_iou,
+  simota_assign_kernel<false><<<B, NTA, smem, s>>>(lc, g, preds, gt, gt_offsets, assigned, matched_iou,
                                                   counters, reinterpret_cast<Cand*>(ws), vcap, AssignExt{});
   return cudaGetLastError();
 }
@@ -519,7 +523,7 @@ cudaError_t launch_simota_assign_ext(const yunet_loss_cfg_dev& lc, int P, const 
     configured = smem;
   }
   AssignExt ext{scores, priors, boxes};
-  simota_assign_kernel<true><<<1, NT, smem, s>>>(lc, g, nullptr, gt, gt_offsets, assigned, matched_iou,
+  simota_assign_kernel<true><<<1, NTA, smem, s>>>(lc, g, nullptr, gt, gt_offsets, assigned, matched_iou,
                                                  counters, reinterpret_cast<Cand*>(ws), vcap, ext);
   return cudaGetLastError();
 }

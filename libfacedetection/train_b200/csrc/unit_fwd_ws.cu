@@ -599,14 +599,16 @@ unit_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap, const UnitFwdArgs a
       if (!ok) break;
       unsigned char* dst = sIn + s * C::STAGE_BYTES + kbo;
       const int gy0 = it.blk * RB - 1, gx0 = it.sx * geo.SW - 1;
-      // two pixels per step: all global loads of both first (memory-level parallelism), then the math
+      // U pixels per step: all their global loads first (memory-level parallelism: the loaders are a
+      // chain of dependent load round trips per block), then the math
+      constexpr int U = 4;
       int pr = p0 / SWH, pc = p0 - pr * SWH;
-      for (int p = p0; p < npx; p += 2 * PPI) {
-        float4 zz[2][4];
-        bool inb[2];
-        int pp[2];
+      for (int p = p0; p < npx; p += U * PPI) {
+        float4 zz[U][MODE == 1 ? 4 : 2];
+        bool inb[U];
+        int pp[U];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < U; ++u) {
           pp[u] = p + u * PPI;
           const int gy = gy0 + pr, gx = gx0 + pc;
           inb[u] = pp[u] < npx && gy >= 0 && gy < a.H && gx >= 0 && gx < a.W;
@@ -630,7 +632,7 @@ unit_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap, const UnitFwdArgs a
           while (pc >= SWH) { pc -= SWH; ++pr; }
         }
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < U; ++u) {
           if (pp[u] >= npx) continue;
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
           if (inb[u]) {
