@@ -271,6 +271,11 @@ class YuNetEngine:
         new buffers runs eagerly (it also sizes every workspace), the second captures, later ones
         replay.  Inputs must stay at the same addresses (a real input pipeline writes into fixed
         device slots, like ``bench.py``'s two double-buffered ones)."""
+        from . import dist_utils
+        if dist_utils.world_size() > 1:
+            # the two NCCL all-reduces of a data-parallel step are not captured (every rank would have to
+            # capture and replay in lock step): launch the kernels individually
+            return self._train_step_impl(img, gt, gt_offsets, lr, momentum, weight_decay, True)
         key = (img.data_ptr(), gt.data_ptr(), gt_offsets.data_ptr(), tuple(img.shape), tuple(gt.shape),
                float(momentum), float(weight_decay))
         if not hasattr(self, '_graphs'):
