@@ -264,7 +264,7 @@ def extra_infer_config(arch, B, S, dev, peak, cpu=True):
     return out
 
 
-def plugin_e2e(arch, B, S, dev, steps, warmup):
+def plugin_e2e(arch, B, S, dev, steps, warmup, optimizer='registry', breakdown=False):
     """The same training step through the mmdet plugin surface (``plugins.YuNet.train_step`` +
     ``torch.optim.SGD``), host buffers, H2D of images / GT lists and D2H of the losses per step."""
     from libfacedetection.train_b200 import plugins, synthetic
@@ -287,7 +287,11 @@ def plugin_e2e(arch, B, S, dev, steps, warmup):
                       max_per_img=-1))
     torch.manual_seed(0)
     m = plugins.DETECTORS.build(cfg).to(dev).train()
-    opt = torch.optim.SGD(m.parameters(), lr=LR, momentum=0.9, weight_decay=0.0005)
+    ocfg = dict(type='SGD', lr=LR, momentum=0.9, weight_decay=0.0005)      # configs/yunet_n.py:1
+    if optimizer == 'registry':      # what mmcv's build_optimizer returns after register_into_mmdet()
+        opt = plugins.OPTIMIZERS.build(ocfg, default_args=dict(params=m.parameters()))
+    else:                            # the stock class on the same parameters
+        opt = torch.optim.SGD(m.parameters(), **{k: v for k, v in ocfg.items() if k != 'type'})
     himg = torch.from_numpy(synthetic.make_images(B, S, 0)).pin_memory()
     gb, gl, gk = synthetic.make_gt(B, S, 0)
     hb = [torch.from_numpy(x).pin_memory() for x in gb]
@@ -318,7 +322,10 @@ def plugin_e2e(arch, B, S, dev, steps, warmup):
         ev.record(main)
     upload(0)
 
+    host = dict(prep=0.0, train_step=0.0, backward=0.0, opt_step=0.0, n=0)
+
     def step():
+        ts = time.perf_counter()
         slot = state['i'] % 2
         state['i'] += 1
         upload(slot ^ 1)
@@ -326,17 +333,25 @@ def plugin_e2e(arch, B, S, dev, steps, warmup):
         db, dk, dl = staged[slot]
         data = dict(img=dimgs[slot], img_metas=[{}] * B, gt_bboxes=list(db), gt_labels=list(dl),
                     gt_keypointss=list(dk))
+        t0 = time.perf_counter()
         opt.zero_grad()
         out = m.train_step(data)              # log_vars: host floats (D2H of the four losses)
+        t1 = time.perf_counter()
         out['loss'].backward()
+        t2 = time.perf_counter()
         opt.step()
+        t3 = time.perf_counter()
         freed[slot].record(main)
+        host['prep'] += t0 - ts; host['train_step'] += t1 - t0; host['backward'] += t2 - t1
+        host['opt_step'] += t3 - t2; host['n'] += 1
         return out
 
     for _ in range(warmup):
         step()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for k in host:
+        host[k] = 0
     e0.record()
     for _ in range(steps):
         step()
@@ -346,9 +361,13 @@ def plugin_e2e(arch, B, S, dev, steps, warmup):
     h2d = himg.numel() * 4 + bb_all.numel() * 4 + kp_all.numel() * 4 + lb_all.numel() * 8
     del m, opt, dimgs, staged
     torch.cuda.empty_cache()
+    # host-side wall time of the four phases of a step (train_step includes the wait for the losses)
+    host_ms = {k: round(1e3 * v / max(host['n'], 1), 3) for k, v in host.items() if k != 'n'}
     return {'value': B / (ms / 1e3), 'unit': UNIT, 'ms_per_step': ms, 'steps': steps,
-            'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 16,
-            'api': 'plugins.YuNet.train_step + loss.backward() + torch.optim.SGD.step (mmdet plugin surface)'}
+            'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 16, 'host_ms': host_ms,
+            'optimizer': ('plugins.SGD (torch.optim.SGD subclass, what the OPTIMIZERS registry builds from '
+                          "dict(type='SGD', ...))" if optimizer == 'registry' else 'torch.optim.SGD'),
+            'api': 'plugins.YuNet.train_step + loss.backward() + optimizer.step() (mmdet plugin surface)'}
 
 
 def plugins_arch(arch):
@@ -666,6 +685,9 @@ def run_ours(args):
         free_cache()
         try:
             e2e_plugin = plugin_e2e(args.arch, B, S, dev, steps=max(5, K // 2), warmup=3)
+            e2e_plugin['torch_sgd'] = {k: v for k, v in plugin_e2e(
+                args.arch, B, S, dev, steps=max(5, K // 2), warmup=3, optimizer='torch').items()
+                if k in ('value', 'ms_per_step', 'host_ms')}
         except Exception as ex:      # reported, never fatal for the headline line
             e2e_plugin = {'error': repr(ex)[:300]}
         extra = {}

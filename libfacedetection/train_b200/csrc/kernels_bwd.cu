@@ -51,6 +51,9 @@ __device__ __forceinline__ float4 ldg4(const float* p) {
 __device__ __forceinline__ float4 lds4(const float* p) {
   return *reinterpret_cast<const float4*>(p);
 }
+__device__ __forceinline__ float2 lds2(const float* p) {
+  return *reinterpret_cast<const float2*>(p);
+}
 __device__ __forceinline__ void sts4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ float4 f4(float v) { return make_float4(v, v, v, v); }
 __device__ __forceinline__ float4 add4(float4 a, float4 b) {
@@ -71,7 +74,7 @@ __device__ __forceinline__ float comp(const float4& v, int i) {
   return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w;
 }
 
-template <int CIN, int COUT>
+template <int CIN, int COUT, int PAIRM = 1>
 struct BwdCfg {
   // interior tile 8 x 16; the 16 -> 16 units (160^2 / 80^2 layers) take 16 x 16 so that the
   // per-tile barriers and load latency are amortised over twice the pixels at equal occupancy
@@ -95,10 +98,17 @@ struct BwdCfg {
   // GEMM3: 4x4 output blocks, pixel-split groups
   static constexpr int NOUT = (COUT / 4) * (CIN / 4);
   static constexpr int G3 = NT / NOUT;
-  // depthwise stage
-  static constexpr int NQ = COUT / 4;
-  static constexpr int RG = NT / (NQ * TW);
+  // depthwise stage: thread = (channel quad, column) x RPT rows; for COUT <= 32 a thread takes a channel
+  // PAIR instead (twice the rows): 22 persistent + 40 transient registers instead of 44 + 76, which is what
+  // lets the two-CTAs-per-SM build (128 registers) run without spilling the gradient accumulators
+  // (the builds with CIN * COUT <= 1024; for COUT = 64 the pair threads walk the 16 columns in two passes)
+  static constexpr bool PAIR = PAIRM != 0 && CIN * COUT <= 1024;
+  static constexpr int NQ = PAIR ? COUT / 2 : COUT / 4;
+  static constexpr int TWP = (NQ * TW <= NT) ? TW : NT / NQ;   // columns per pass
+  static constexpr int CPASS = TW / TWP;
+  static constexpr int RG = NT / (NQ * TWP);
   static constexpr int RPT = TH / RG;
+  static_assert(RG >= 1 && TH % RG == 0 && TW % TWP == 0 && (PAIR || CPASS == 1), "depthwise mapping");
   // epilogue
   static constexpr int QI = CIN / 4;
   static constexpr int EPT = TP * QI / NT;          // items per thread (hi-res)
@@ -109,9 +119,9 @@ struct BwdCfg {
   static_assert(TP % NPG1 == 0 && TP % NPG2 == 0, "gemm mapping");
 };
 
-template <int CIN, int COUT, int MODE, int HAS_BN, int OCC>
+template <int CIN, int COUT, int MODE, int HAS_BN, int OCC, int PAIRM>
 __global__ void __launch_bounds__(NT, OCC) unit_bwd_kernel(const UnitBwdArgs a) {
-  using C = BwdCfg<CIN, COUT>;
+  using C = BwdCfg<CIN, COUT, PAIRM>;
   extern __shared__ float4 smem_raw[];
   float* smem = reinterpret_cast<float*>(smem_raw);
   float* sG = smem;                        // [C::HP][COUT]
@@ -169,12 +179,15 @@ __global__ void __launch_bounds__(NT, OCC) unit_bwd_kernel(const UnitBwdArgs a) 
   // ---- persistent accumulators
   // depthwise-stage mapping
   const int dq = tid % C::NQ;
-  const int dx = (tid / C::NQ) % C::TW;
-  const int dr0 = (tid / (C::NQ * C::TW)) * C::RPT;
-  float4 gw2[9];
+  const int dx0 = (tid / C::NQ) % C::TWP;
+  const int dr0 = (tid / (C::NQ * C::TWP)) * C::RPT;
+  float4 gw2[C::PAIR ? 1 : 9];
+  float2 pw2[C::PAIR ? 9 : 1];      // PAIR: the channel pair's nine tap gradients
 #pragma unroll
-  for (int k = 0; k < 9; ++k) gw2[k] = f4(0.f);
-  float4 gb2 = f4(0.f), gb1 = f4(0.f);
+  for (int k = 0; k < (C::PAIR ? 1 : 9); ++k) gw2[k] = f4(0.f);
+#pragma unroll
+  for (int k = 0; k < (C::PAIR ? 9 : 1); ++k) pw2[k] = make_float2(0.f, 0.f);
+  float4 gb2 = f4(0.f), gb1 = f4(0.f);   // PAIR: .x/.y used
   // GEMM3 mapping
   const int o3 = tid % C::NOUT;
   const int g3 = tid / C::NOUT;
@@ -263,11 +276,21 @@ __global__ void __launch_bounds__(NT, OCC) unit_bwd_kernel(const UnitBwdArgs a) 
       const float* dimg = a.dout + (long long)b * a.dout_batch_stride;
       const float* zimg = HAS_BN ? a.zout + (long long)b * a.H * a.W * COUT : nullptr;
       if (PF) cp_async_wait<0>();       // a thread reads back exactly the chunks it copied
+      // NT % Q == 0: a thread's items all belong to channel quad tid % Q -- its BN-backward constants
+      // are read once per tile instead of once per item
+      static_assert(NT % Q == 0, "channel quad of a thread's items");
+      const int q = tid % Q;
+      float4 gs, m1, m2, mu, rs;
+      if (HAS_BN) {
+        gs = lds4(sCo + 0 * COUT + q * 4); m1 = lds4(sCo + 1 * COUT + q * 4);
+        m2 = lds4(sCo + 2 * COUT + q * 4); mu = lds4(sCo + 3 * COUT + q * 4);
+        rs = lds4(sCo + 4 * COUT + q * 4);
+      }
 #pragma unroll 4
       for (int it = 0; it < (C::HP * Q + NT - 1) / NT; ++it) {
         const int i = tid + it * NT;
         if (i >= C::HP * Q) break;
-        const int pix = i / Q, q = i % Q;
+        const int pix = i / Q;
         const int gy = y0 + pix / C::HW - 1, gx = x0 + pix % C::HW - 1;
         float4 g = f4(0.f);
         if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) {
@@ -275,9 +298,6 @@ __global__ void __launch_bounds__(NT, OCC) unit_bwd_kernel(const UnitBwdArgs a) 
           g = PF ? lds4(sRawD + pix * COUT + q * 4) : ldg4(dimg + off);
           if (HAS_BN) {
             const float4 z = PF ? lds4(sRawZ + pix * COUT + q * 4) : ldg4(zimg + off);
-            const float4 gs = lds4(sCo + 0 * COUT + q * 4), m1 = lds4(sCo + 1 * COUT + q * 4);
-            const float4 m2 = lds4(sCo + 2 * COUT + q * 4), mu = lds4(sCo + 3 * COUT + q * 4);
-            const float4 rs = lds4(sCo + 4 * COUT + q * 4);
             g.x = gs.x * (g.x - m1.x - (z.x - mu.x) * rs.x * m2.x);
             g.y = gs.y * (g.y - m1.y - (z.y - mu.y) * rs.y * m2.y);
             g.z = gs.z * (g.z - m1.z - (z.z - mu.z) * rs.z * m2.z);
@@ -374,7 +394,49 @@ __global__ void __launch_bounds__(NT, OCC) unit_bwd_kernel(const UnitBwdArgs a) 
     __syncthreads();
 
     // ---- S2: depthwise backward: dy (in place over y), dW2, db2, db1
-    {
+    if constexpr (C::PAIR) {
+      float2 w2r[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) w2r[k] = lds2(sW2 + k * COUT + dq * 2);
+#pragma unroll 1
+      for (int cp = 0; cp < C::CPASS; ++cp) {
+      const int dx = dx0 + cp * C::TWP;
+      float2 ra[3], rb[3], rc[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        ra[d] = lds2(sG + ((dr0 + 0) * C::HW + dx + d) * COUT + dq * 2);
+        rb[d] = lds2(sG + ((dr0 + 1) * C::HW + dx + d) * COUT + dq * 2);
+      }
+      const int gx = x0 + dx;
+#pragma unroll
+      for (int i = 0; i < C::RPT; ++i) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+          rc[d] = lds2(sG + ((dr0 + i + 2) * C::HW + dx + d) * COUT + dq * 2);
+        const int r = dr0 + i;
+        const int pix = r * C::TW + dx;
+        const bool in = (y0 + r) < a.H && gx < a.W;
+        const float2 y = lds2(sY + pix * C::YS + dq * 2);
+        float2 dy = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          fma2(dy.x, dy.y, w2r[0 * 3 + kx].x, w2r[0 * 3 + kx].y, rc[2 - kx].x, rc[2 - kx].y);
+          fma2(dy.x, dy.y, w2r[1 * 3 + kx].x, w2r[1 * 3 + kx].y, rb[2 - kx].x, rb[2 - kx].y);
+          fma2(dy.x, dy.y, w2r[2 * 3 + kx].x, w2r[2 * 3 + kx].y, ra[2 - kx].x, ra[2 - kx].y);
+          fma2(pw2[0 * 3 + kx].x, pw2[0 * 3 + kx].y, y.x, y.y, rc[2 - kx].x, rc[2 - kx].y);
+          fma2(pw2[1 * 3 + kx].x, pw2[1 * 3 + kx].y, y.x, y.y, rb[2 - kx].x, rb[2 - kx].y);
+          fma2(pw2[2 * 3 + kx].x, pw2[2 * 3 + kx].y, y.x, y.y, ra[2 - kx].x, ra[2 - kx].y);
+        }
+        gb2.x += rb[1].x; gb2.y += rb[1].y;
+        if (!in) dy = make_float2(0.f, 0.f);
+        gb1.x += dy.x; gb1.y += dy.y;
+        *reinterpret_cast<float2*>(sY + pix * C::YS + dq * 2) = dy;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { ra[d] = rb[d]; rb[d] = rc[d]; }
+      }
+      }
+    } else {
+      const int dx = dx0;
       float4 w2r[9];
 #pragma unroll
       for (int k = 0; k < 9; ++k) w2r[k] = lds4(sW2 + k * COUT + dq * 4);
@@ -578,14 +640,25 @@ __global__ void __launch_bounds__(NT, OCC) unit_bwd_kernel(const UnitBwdArgs a) 
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) atomicAdd(sRed + (co3 + i) * CIN + ci3 + j, gw1[i][j]);
-    constexpr int NQ = C::NQ;   // lanes l, l+NQ, ... of a warp share a channel quad: reduce first
-    float vals[44];
+    constexpr int NQ = C::NQ;   // lanes l, l+NQ, ... of a warp share a channel quad (pair): reduce first
+    constexpr int CPL = C::PAIR ? 2 : 4;          // channels per lane
+    float vals[11 * CPL];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) { vals[k * 4] = gw2[k].x; vals[k * 4 + 1] = gw2[k].y; vals[k * 4 + 2] = gw2[k].z; vals[k * 4 + 3] = gw2[k].w; }
-    vals[36] = gb2.x; vals[37] = gb2.y; vals[38] = gb2.z; vals[39] = gb2.w;
-    vals[40] = gb1.x; vals[41] = gb1.y; vals[42] = gb1.z; vals[43] = gb1.w;
+    for (int k = 0; k < 9; ++k) {
+      if constexpr (C::PAIR) {
+        vals[k * 2] = pw2[k].x; vals[k * 2 + 1] = pw2[k].y;
+      } else {
+        vals[k * 4] = gw2[k].x; vals[k * 4 + 1] = gw2[k].y; vals[k * 4 + 2] = gw2[k].z; vals[k * 4 + 3] = gw2[k].w;
+      }
+    }
+    vals[9 * CPL] = gb2.x; vals[9 * CPL + 1] = gb2.y;
+    vals[10 * CPL] = gb1.x; vals[10 * CPL + 1] = gb1.y;
+    if constexpr (!C::PAIR) {
+      vals[38] = gb2.z; vals[39] = gb2.w;
+      vals[42] = gb1.z; vals[43] = gb1.w;
+    }
 #pragma unroll
-    for (int v = 0; v < 44; ++v) {
+    for (int v = 0; v < 11 * CPL; ++v) {
 #pragma unroll
       for (int o = 16; o >= NQ; o >>= 1) vals[v] += __shfl_xor_sync(0xffffffffu, vals[v], o);
     }
@@ -593,11 +666,11 @@ __global__ void __launch_bounds__(NT, OCC) unit_bwd_kernel(const UnitBwdArgs a) 
 #pragma unroll
       for (int k = 0; k < 9; ++k)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) atomicAdd(sRed + NW1 + COUT + (dq * 4 + c) * 9 + k, vals[k * 4 + c]);
+        for (int c = 0; c < CPL; ++c) atomicAdd(sRed + NW1 + COUT + (dq * CPL + c) * 9 + k, vals[k * CPL + c]);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        atomicAdd(sRed + NW1 + 10 * COUT + dq * 4 + c, vals[36 + c]);   // gb2
-        atomicAdd(sRed + NW1 + dq * 4 + c, vals[40 + c]);               // gb1
+      for (int c = 0; c < CPL; ++c) {
+        atomicAdd(sRed + NW1 + 10 * COUT + dq * CPL + c, vals[9 * CPL + c]);   // gb2
+        atomicAdd(sRed + NW1 + dq * CPL + c, vals[10 * CPL + c]);              // gb1
       }
     }
     __syncthreads();
@@ -799,13 +872,13 @@ __global__ void bn_param_grads_kernel(const BnFinalizeArgs a, const double* dsum
   grad[a.beta_off[i] + c] = (float)dsum[a.ch_off[i] + c];
 }
 
-template <int CIN, int COUT, int MODE, int HAS_BN, int OCC>
+template <int CIN, int COUT, int MODE, int HAS_BN, int OCC, int PAIRM = 1>
 cudaError_t launch_unit_bwd_o(const UnitBwdArgs& a, int num_sms, cudaStream_t s) {
-  using C = BwdCfg<CIN, COUT>;
+  using C = BwdCfg<CIN, COUT, PAIRM>;
   constexpr int RAWF = (HAS_BN ? 2 : 1) * C::HP * COUT;
   constexpr bool PF = OCC == 2 && (C::SMEM_FLOATS + RAWF) * 4 <= 112 * 1024;      // as in the kernel
   const size_t smem = sizeof(float) * (C::SMEM_FLOATS + (PF ? RAWF : 0));
-  auto kern = unit_bwd_kernel<CIN, COUT, MODE, HAS_BN, OCC>;
+  auto kern = unit_bwd_kernel<CIN, COUT, MODE, HAS_BN, OCC, PAIRM>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -823,15 +896,20 @@ cudaError_t launch_unit_bwd_o(const UnitBwdArgs& a, int num_sms, cudaStream_t s)
   return launch_reduce_partials(a.partial, grid, COUT * CIN + 11 * COUT, a.gw1, s);
 }
 
-// CTAs per SM: two for the small-weight units (128 registers, the persistent gradient accumulators
-// spill ~400 B) -- YUNET_BWD_OCC=1 selects the spill-free single-CTA build of the 16-channel units
-// (development knob, read once)
+// CTAs per SM: two for the small-weight units (128 registers; with the channel-pair depthwise mapping
+// the persistent gradient accumulators no longer spill).  Development knobs, read once:
+// YUNET_BWD_OCC=1 selects the single-CTA build of the 16-channel units, YUNET_BWD_QUAD=1 the round-1
+// quad mapping of the depthwise stage (spills ~500 B per thread at 128 registers) for A/B timing.
 template <int CIN, int COUT, int MODE, int HAS_BN>
 cudaError_t launch_unit_bwd_t(const UnitBwdArgs& a, int num_sms, cudaStream_t s) {
   constexpr int DEF = (CIN * COUT <= 1024) ? 2 : 1;
   if (CIN == 16 && DEF == 2) {
     static const int occ = [] { const char* e = getenv("YUNET_BWD_OCC"); return e ? atoi(e) : 0; }();
     if (occ == 1) return launch_unit_bwd_o<CIN, COUT, MODE, HAS_BN, (CIN == 16 ? 1 : DEF)>(a, num_sms, s);
+  }
+  if (DEF == 2) {
+    static const int quad = [] { const char* e = getenv("YUNET_BWD_QUAD"); return e ? atoi(e) : 0; }();
+    if (quad == 1) return launch_unit_bwd_o<CIN, COUT, MODE, HAS_BN, DEF, (DEF == 2 ? 0 : 1)>(a, num_sms, s);
   }
   return launch_unit_bwd_o<CIN, COUT, MODE, HAS_BN, DEF>(a, num_sms, s);
 }

@@ -9,6 +9,8 @@ config written for the reference builds them unchanged:
   ``YuNet_Head``      mmdet/models/dense_heads/yunet_head.py:16-604
   ``SimOTAAssigner``  mmdet/core/bbox/assigners/sim_ota_assigner.py:12-36
   ``YuNet``           mmdet/models/detectors/yunet.py:7-86 (+ single_stage.py:17-57, base.py:184-252)
+  ``SGD``             ``optimizer = dict(type='SGD', ...)`` (configs/yunet_n.py:1) as mmcv's
+                      ``build_optimizer`` resolves it: ``torch.optim.SGD`` with a one-launch fused step
 
 Execution is fused across the three modules: ``YuNetBackbone.forward`` returns a light
 ``FusedFeatures`` handle that ``TFPN.forward`` passes through and ``YuNet_Head`` consumes — the
@@ -17,6 +19,8 @@ reference's own ``SingleStageDetector.extract_feat`` -> ``bbox_head.forward_trai
 The torch modules only *hold* the parameters (as views into the engine's flat bucket); no torch
 operator runs on the hot path.
 """
+import weakref
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -62,6 +66,7 @@ NECKS = Registry('neck')
 HEADS = Registry('head')
 DETECTORS = Registry('detector')
 BBOX_ASSIGNERS = Registry('bbox_assigner')
+OPTIMIZERS = Registry('optimizer')
 
 
 def register_into_mmdet(force=True):
@@ -72,6 +77,11 @@ def register_into_mmdet(force=True):
     for cls in (YuNetBackbone, TFPN, YuNet_Head, YuNet):
         MODELS.register_module(name=cls.__name__, force=force, module=cls)
     MM_ASSIGNERS.register_module(name='SimOTAAssigner', force=force, module=SimOTAAssigner)
+    try:    # mmcv.runner.optimizer.builder registers the torch optimizers under their class names
+        from mmcv.runner.optimizer.builder import OPTIMIZERS as MM_OPTIMIZERS
+        MM_OPTIMIZERS.register_module(name='SGD', force=force, module=SGD)
+    except ImportError:
+        pass
 
 
 # --------------------------------------------------------------------------------- containers
@@ -424,9 +434,7 @@ class _FusedLoss(torch.autograd.Function):
         # every parameter gets a VIEW of the flat gradient bucket (no copies): autograd's
         # AccumulateGrad adopts it as ``.grad`` when the gradient was None (zero_grad(set_to_none=True),
         # torch's default) and adds it in place otherwise; the bucket is rewritten by the next backward
-        views = core.param_views(core.grads)
-        grads = [views[k] for k in glue.names]
-        return (None, None, None, None) + tuple(grads)
+        return (None, None, None, None) + glue.grad_views
 
 
 def pack_gt_csr_device(gt_bboxes, gt_keypointss, device):
@@ -440,8 +448,11 @@ def pack_gt_csr_device(gt_bboxes, gt_keypointss, device):
     total = int(sum(counts))
     gt = torch.empty(max(total, 0), 19, device=device, dtype=torch.float32)
     if total:
-        bb = torch.cat([b.reshape(-1, 4) for b in gt_bboxes]).to(device=device, dtype=torch.float32)
-        kp = torch.cat([k.reshape(-1, 5, 3) for k in gt_keypointss]).to(device=device, dtype=torch.float32)
+        # (a metadata call per image costs more than the copy at 256 images: reshape only odd shapes)
+        bb = torch.cat([b if b.dim() == 2 else b.reshape(-1, 4) for b in gt_bboxes])
+        kp = torch.cat([k if k.dim() == 3 else k.reshape(-1, 5, 3) for k in gt_keypointss])
+        bb = bb.to(device=device, dtype=torch.float32)
+        kp = kp.to(device=device, dtype=torch.float32)
         gt[:, :4] = bb
         gt[:, 4:14] = kp[:, :, :2].reshape(-1, 10)
         gt[:, 14:19] = kp[:, :, 2]
@@ -462,7 +473,14 @@ class _Glue:
         self.core = YuNetEngine(arch, device=dev, loss_cfg=head.loss_cfg)
         self.modules = {'backbone': backbone, 'neck': neck, 'bbox_head': head}
         self.names = [n for n, _, _ in self.core.param_table]
+        gv = self.core.param_views(self.core.grads)
+        mv = self.core.param_views(self.core.momentum_buf)
+        self.grad_views = tuple(gv[k] for k in self.names)        # handed out by every backward
+        self.momentum_views = tuple(mv[k] for k in self.names)    # ``SGD.state[p]['momentum_buffer']``
+        self.grad_ptrs = [v.data_ptr() for v in self.grad_views]
+        self.momentum_ptrs = [v.data_ptr() for v in self.momentum_views]
         self._adopt()
+        _LIVE_GLUES.add(self)
 
     def _named(self):
         p, b = {}, {}
@@ -491,6 +509,13 @@ class _Glue:
                 owner.running_mean = rm
                 owner.running_var = rv
         self.params = [p[k] for k in self.names]
+        self.param_ptrs = [q.data_ptr() for q in self.params]
+        # per-step bookkeeping without walking the module tree by name: the parameters in module
+        # order with the addresses they must keep, and the BatchNorm step counters
+        self._mod_params = [q for m in self.modules.values() for q in m.parameters()]
+        self._mod_ptrs = [q.data_ptr() for q in self._mod_params]
+        self._nbt = [mod.num_batches_tracked for m in self.modules.values() for mod in m.modules()
+                     if isinstance(mod, nn.BatchNorm2d)]
 
     def _resolve(self, dotted):
         prefix, rest = dotted.split('.', 1)
@@ -502,23 +527,26 @@ class _Glue:
     def sync_from_modules(self):
         """Re-adopt if something (``.to()``, ``load_state_dict`` on a fresh tensor) re-pointed a
         parameter away from the bucket."""
-        views = self.core.param_views()
-        p, _ = self._named()
-        if any(p[k].data_ptr() != views[k].data_ptr() for k in self.names):
+        cur = [q for m in self.modules.values() for q in m.parameters()]
+        same = len(cur) == len(self._mod_params)
+        if same:
+            for q, q0, ptr in zip(cur, self._mod_params, self._mod_ptrs):
+                if q is not q0 or q.data_ptr() != ptr:
+                    same = False
+                    break
+        if not same:
             self._adopt()
 
     def losses(self, img, gt_bboxes, gt_keypointss):
         self.sync_from_modules()
         gt, offs = pack_gt_csr_device(gt_bboxes, gt_keypointss, img.device)
         l = _FusedLoss.apply(self, img.contiguous(), gt, offs, *self.params)
-        for m in self.modules.values():
-            for mod in m.modules():
-                if isinstance(mod, nn.BatchNorm2d):
-                    mod.num_batches_tracked += 1
+        torch._foreach_add_(self._nbt, 1)       # every BatchNorm2d.num_batches_tracked, one launch
         return dict(loss_cls=l[0], loss_bbox=l[1], loss_obj=l[2], loss_kps=l[3])
 
 
 _ENGINES = {}
+_LIVE_GLUES = weakref.WeakSet()     # looked up by ``SGD`` to find the bucket its parameters alias
 
 
 def _engine_for(backbone, neck, head):
@@ -539,6 +567,72 @@ def _any_engine(device):
         e = YuNetEngine('yunet_n', device=device)
         _ENGINES[str(device)] = e
     return e
+
+
+class SGD(torch.optim.SGD):
+    """``torch.optim.SGD`` — what mmcv's ``build_optimizer`` makes of the reference's
+    ``optimizer = dict(type='SGD', lr=0.01, momentum=0.9, weight_decay=0.0005)`` (configs/yunet_n.py:1,
+    mmdet/apis/train.py:117) — whose ``step()`` is ONE ``yunet_sgd_step`` launch over the flat bucket when
+    that is exactly what the stock step would compute: a single param group without dampening /
+    nesterov / maximize whose parameters are all the views of one engine's bucket and whose ``.grad``
+    tensors are all the matching views of its gradient bucket (what ``_FusedLoss.backward`` hands out;
+    in-place edits such as ``clip_grad_norm_`` or DDP's averaging land in the bucket and are honoured).
+    Anything else (a ``None`` gradient, accumulated gradients in foreign storage, several groups)
+    takes ``torch.optim.SGD.step`` unchanged.  ``state[p]['momentum_buffer']`` are views of the engine's
+    flat momentum bucket, so ``state_dict()`` / ``load_state_dict()`` keep the reference checkpoint
+    layout and both paths share one state (a zero buffer reproduces torch's first step ``buf = grad``)."""
+
+    def _fused_glue(self):
+        if len(self.param_groups) != 1:
+            return None
+        g = self.param_groups[0]
+        if g.get('dampening', 0) != 0 or g.get('nesterov', False) or g.get('maximize', False):
+            return None
+        ps = g['params']
+        glue = getattr(self, '_b200_glue_ref', None)
+        glue = glue() if glue is not None else None
+        if glue is None or len(glue.params) != len(ps):
+            glue = None
+            ids = {id(q) for q in ps}
+            for cand in list(_LIVE_GLUES):
+                if len(cand.params) == len(ps) and all(id(q) in ids for q in cand.params):
+                    glue = cand
+                    break
+            if glue is None:
+                return None
+            self._b200_glue_ref = weakref.ref(glue)
+        for q, pptr, gptr in zip(glue.params, glue.param_ptrs, glue.grad_ptrs):
+            gr = q.grad
+            if gr is None or gr.data_ptr() != gptr or q.data_ptr() != pptr:
+                return None
+        return glue
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        glue = self._fused_glue()
+        if glue is None:
+            return super().step(closure)
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        g = self.param_groups[0]
+        if g['momentum'] != 0:
+            # one shared momentum state: whatever a stock step or load_state_dict left in ``state`` is
+            # moved into the flat bucket, and ``state`` then holds the bucket's views
+            for q, view, mptr in zip(glue.params, glue.momentum_views, glue.momentum_ptrs):
+                st = self.state[q]
+                buf = st.get('momentum_buffer')
+                if buf is None or buf.data_ptr() != mptr:
+                    if buf is not None:
+                        view.copy_(buf.reshape(view.shape))
+                    st['momentum_buffer'] = view
+        glue.core.sgd_step(lr=float(g['lr']), momentum=float(g['momentum']),
+                           weight_decay=float(g['weight_decay']), grad_scale=1.0)
+        return loss
+
+
+OPTIMIZERS.register_module(module=SGD)
 
 
 @DETECTORS.register_module()

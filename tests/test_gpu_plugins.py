@@ -44,12 +44,20 @@ def test_feature_test_and_simple_test(arch):
     assert len(res) == 1 and res[0][0].shape == (g['dets'].shape[0], 5)
 
 
+@pytest.mark.parametrize('opt_cls', ['torch', 'plugin'])
 @pytest.mark.parametrize('arch,seed', [('yunet_n', 0), ('yunet_s', 1)])
-def test_train_step_through_autograd_and_torch_sgd(arch, seed):
+def test_train_step_through_autograd_and_torch_sgd(arch, seed, opt_cls):
+    """``opt_cls``: the stock ``torch.optim.SGD`` and the ``SGD`` the plugin registry resolves the
+    reference's ``optimizer = dict(type='SGD', ...)`` to (same class hierarchy, one-launch step)."""
     g = np.load(os.path.join(GOLDEN, f'train_{arch}_b4.npz'))
     B, size = int(g['B']), int(g['size'])
     m = _model(arch).train()
-    opt = torch.optim.SGD(m.parameters(), lr=0.01, momentum=0.9, weight_decay=0.0005)
+    if opt_cls == 'torch':
+        opt = torch.optim.SGD(m.parameters(), lr=0.01, momentum=0.9, weight_decay=0.0005)
+    else:
+        opt = plugins.OPTIMIZERS.build(dict(type='SGD', lr=0.01, momentum=0.9, weight_decay=0.0005),
+                                       default_args=dict(params=m.parameters()))
+        assert type(opt) is plugins.SGD
     img = torch.from_numpy(synthetic.make_images(B, size, seed)).cuda()
     gb, gl, gk = synthetic.make_gt(B, size, seed)
     data = dict(img=img, img_metas=[{}] * B,
@@ -88,7 +96,13 @@ def test_train_step_through_autograd_and_torch_sgd(arch, seed):
     views = core.param_views(core.grads)
     for k, p in m.named_parameters():
         assert torch.equal(p.grad, views[k]), k
+    if opt_cls == 'plugin':
+        assert opt._fused_glue() is not None          # the step below is the one-launch path
     opt.step()
+    if opt_cls == 'plugin':
+        mom = core.param_views(core.momentum_buf)
+        for k, p in m.named_parameters():             # optimizer state = views of the flat momentum bucket
+            assert opt.state[p]['momentum_buffer'].data_ptr() == mom[k].data_ptr(), k
     sd = m.state_dict()
     for k, _ in m.named_parameters():
         ref = torch.from_numpy(g['after/' + k])

@@ -110,3 +110,137 @@ def test_register_into_mmdet_builds_the_plugins_from_the_reference_config():
         for k, v in saved.items():
             MODELS.register_module(name=k, force=True, module=v)
         MM_ASSIGNERS.register_module(name='SimOTAAssigner', force=True, module=saved_a)
+
+
+# ------------------------------------------------------------------------------ plugins.SGD host logic
+class _StubCore:
+    """The flat buckets of an engine on the CPU with ``sgd_step`` restated in torch (csrc/sgd.cu)."""
+
+    def __init__(self, shapes):
+        self.shapes = shapes
+        n = sum(int(np.prod(s)) for s in shapes)
+        self.params, self.grads, self.momentum_buf = torch.zeros(n), torch.zeros(n), torch.zeros(n)
+        self.calls = 0
+
+    def views(self, bucket):
+        out, off = [], 0
+        for s in self.shapes:
+            n = int(np.prod(s))
+            out.append(bucket[off:off + n].view(s))
+            off += n
+        return tuple(out)
+
+    def sgd_step(self, lr, momentum, weight_decay, grad_scale):
+        self.calls += 1
+        g = self.grads * grad_scale + weight_decay * self.params
+        self.momentum_buf.mul_(momentum).add_(g)
+        self.params.sub_(lr * self.momentum_buf)
+
+
+class _StubGlue:
+    def __init__(self, shapes, seed=0):
+        self.core = _StubCore(shapes)
+        g = torch.Generator().manual_seed(seed)
+        self.core.params.copy_(torch.randn(self.core.params.numel(), generator=g))
+        self.params = [torch.nn.Parameter(v) for v in self.core.views(self.core.params)]
+        for q, v in zip(self.params, self.core.views(self.core.params)):
+            q.data = v
+        self.grad_views = self.core.views(self.core.grads)
+        self.momentum_views = self.core.views(self.core.momentum_buf)
+        self.param_ptrs = [q.data_ptr() for q in self.params]
+        self.grad_ptrs = [v.data_ptr() for v in self.grad_views]
+        self.momentum_ptrs = [v.data_ptr() for v in self.momentum_views]
+        plugins._LIVE_GLUES.add(self)
+
+    def backward(self, seed):
+        g = torch.Generator().manual_seed(100 + seed)
+        self.core.grads.copy_(torch.randn(self.core.grads.numel(), generator=g))
+        for q, v in zip(self.params, self.grad_views):
+            q.grad = v
+
+
+SHAPES = [(4, 3, 1, 1), (4,), (4, 1, 3, 3), (4,), (7,)]
+KW = dict(lr=0.01, momentum=0.9, weight_decay=0.0005)
+
+
+def test_fused_sgd_equals_torch_sgd_and_shares_the_momentum_state():
+    ga, gb = _StubGlue(SHAPES), _StubGlue(SHAPES)
+    fused = plugins.SGD(ga.params, **KW)
+    stock = torch.optim.SGD([torch.nn.Parameter(q.detach().clone()) for q in gb.params], **KW)
+    for it in range(4):
+        ga.backward(it)
+        gb.backward(it)
+        for q, v in zip(stock.param_groups[0]['params'], gb.grad_views):
+            q.grad = v.clone()
+        fused.step()
+        stock.step()
+        for a, b in zip(ga.params, stock.param_groups[0]['params']):
+            assert torch.allclose(a, b, rtol=1e-6, atol=1e-7)
+    assert ga.core.calls == 4                               # every step took the one-launch path
+    for q, view in zip(ga.params, ga.momentum_views):       # state holds the bucket's views
+        assert fused.state[q]['momentum_buffer'].data_ptr() == view.data_ptr()
+    for a, b in zip(ga.params, stock.param_groups[0]['params']):
+        assert torch.allclose(fused.state[a]['momentum_buffer'], stock.state[b]['momentum_buffer'],
+                              rtol=1e-6, atol=1e-7)
+    # state_dict round trip into a fresh optimizer (resume): buffers are re-homed into the bucket
+    import copy
+    sd = copy.deepcopy(fused.state_dict())      # what torch.save / torch.load hand back
+    gc = _StubGlue(SHAPES)
+    gc.core.params.copy_(ga.core.params)
+    resumed = plugins.SGD(gc.params, **KW)
+    resumed.load_state_dict(sd)
+    ga.backward(9); gc.backward(9)
+    fused.step(); resumed.step()
+    assert gc.core.calls == 1
+    assert torch.allclose(gc.core.params, ga.core.params, rtol=1e-6, atol=1e-7)
+    assert torch.allclose(gc.core.momentum_buf, ga.core.momentum_buf, rtol=1e-6, atol=1e-7)
+
+
+def test_fused_sgd_falls_back_to_the_stock_step():
+    # a None gradient, a gradient in foreign storage, several groups, nesterov: torch.optim.SGD.step
+    for case in ('none_grad', 'foreign_grad', 'two_groups', 'nesterov'):
+        ga, gb = _StubGlue(SHAPES), _StubGlue(SHAPES)
+        kw = dict(KW, nesterov=True) if case == 'nesterov' else KW
+        if case == 'two_groups':
+            mk = lambda ps: [dict(params=ps[:2]), dict(params=ps[2:], weight_decay=0.0)]
+        else:
+            mk = lambda ps: ps
+        stock_params = [torch.nn.Parameter(q.detach().clone()) for q in gb.params]
+        fused, stock = plugins.SGD(mk(ga.params), **kw), torch.optim.SGD(mk(stock_params), **kw)
+        for it in range(2):
+            ga.backward(it)
+            for q, v in zip(stock_params, ga.grad_views):
+                q.grad = v.clone()
+            if case == 'none_grad':
+                ga.params[1].grad = None
+                stock_params[1].grad = None
+            if case == 'foreign_grad':
+                ga.params[2].grad = ga.params[2].grad.clone()
+            fused.step()
+            stock.step()
+        assert ga.core.calls == 0, case
+        for a, b in zip(ga.params, stock_params):
+            assert torch.equal(a.detach(), b.detach()), case
+    # and a fused step after stock steps picks their momentum buffers up
+    ga, gb = _StubGlue(SHAPES), _StubGlue(SHAPES)
+    stock_params = [torch.nn.Parameter(q.detach().clone()) for q in gb.params]
+    fused, stock = plugins.SGD(ga.params, **KW), torch.optim.SGD(stock_params, **KW)
+    for it in range(3):
+        ga.backward(it)
+        for q, v in zip(stock_params, ga.grad_views):
+            q.grad = v.clone()
+        if it == 0:
+            ga.params[0].grad = ga.params[0].grad.clone()       # forces the stock path once
+        fused.step()
+        stock.step()
+    assert ga.core.calls == 2
+    for a, b in zip(ga.params, stock_params):
+        assert torch.allclose(a, b, rtol=1e-6, atol=1e-7)
+
+
+def test_optimizer_registry_builds_the_fused_sgd_from_the_reference_config():
+    # configs/yunet_n.py:1  optimizer = dict(type='SGD', lr=0.01, momentum=0.9, weight_decay=0.0005)
+    ga = _StubGlue(SHAPES)
+    opt = plugins.OPTIMIZERS.build(dict(type='SGD', lr=0.01, momentum=0.9, weight_decay=0.0005),
+                                   default_args=dict(params=ga.params))
+    assert type(opt) is plugins.SGD and isinstance(opt, torch.optim.SGD)
