@@ -1,3 +1,6 @@
+// EXPERIMENTAL variant of unit_bwd_st.cu (selected with YUNET_ST_GW=1): the BatchNorm-backward pass of the
+// output gradient runs on four dedicated warps one step ahead of the main warps (setmaxnreg-rebalanced).
+//
 // Fused ConvDPUnit backward (64 -> 64 channels, BatchNorm on the output) on STRIPS (sm_100a): the
 // tcgen05 kernel of unit_bwd_tc.cu with the tile geometry of the streaming forward kernel.
 //
@@ -23,7 +26,6 @@
 //   warp-uniform operands (TMEM base 0), i.e. back-to-back UTCHMMA.
 // Same math as unit_bwd_kernel (kernels_bwd.cu); semantics: autograd of yunet_layer.py:30-36.
 #include <cstdio>
-#include <cstdlib>
 #include <cstring>
 
 #include "kernels.h"
@@ -38,7 +40,9 @@ namespace {
 
 using namespace tc;
 
-constexpr int NT = 256;
+constexpr int NT = 256;           // main warps: conversions, depthwise backward, epilogue, MMA issue
+constexpr int NTG = 128;          // g warps: BatchNorm backward of the output gradient, one step ahead
+constexpr int NTT = NT + NTG;
 constexpr int C64 = 64;
 constexpr uint32_t TILE_BYTES = 128 * C64 * 4;   // 32 KB
 constexpr uint32_t TMEM_COLS = 512;
@@ -67,6 +71,15 @@ __device__ __forceinline__ bool elect_one_b() {
   uint32_t p;
   asm volatile("{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\tselp.u32 %0, 1, 0, pe;\n\t}" : "=r"(p));
   return p != 0;
+}
+
+// barriers of the 256 main threads only (the g warps run their own loop)
+__device__ __forceinline__ void msync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ bool msync_and(bool p) {
+  uint32_t r;
+  asm volatile("{\n\t.reg .pred q, pr;\n\tsetp.ne.u32 q, %1, 0;\n\tbar.red.and.pred pr, 1, 256, q;\n\tselp.u32 %0, 1, 0, pr;\n\t}"
+               : "=r"(r) : "r"((uint32_t)(p ? 1 : 0)) : "memory");
+  return r != 0;
 }
 
 struct Off {
@@ -143,8 +156,8 @@ __device__ __forceinline__ Coef4 bn_coef_tc(const BnRef& r, int c) {
 }
 
 template <int MODE, int RBT>
-__global__ void __launch_bounds__(NT, 1)
-unit_bwd_st_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_du,
+__global__ void __launch_bounds__(NTT, 1)
+unit_bwd_st_gw_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_du,
                    const __grid_constant__ CUtensorMap tmap_zo, const UnitBwdArgs a, const StripB geo, int* status) {
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
   unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
@@ -158,10 +171,11 @@ unit_bwd_st_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
   float* sCa = reinterpret_cast<float*>(smem + Off::CA);
   float* sCb = reinterpret_cast<float*>(smem + Off::CB);
   float* sCo = reinterpret_cast<float*>(smem + Off::CO);
-  // [0] z_in, [1] mma1, [2] mma2, [3] mma3 (dW1): one completion per REAL block; [4] du, [5] z_out:
-  // one completion per step (real or priming)
+  // [0] z_in, [1] mma1, [2] mma2, [3] mma3 (dW1): one completion per REAL block; per step (real or
+  // priming): [4] du landed (TMA), [5] g ready (one arrival per g warp), [6] g consumed (one arrival per
+  // main warp: the g warps may refill the buffer with the next step's du)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Off::BAR);
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 6);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 7);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int warp_u = (int)warp_uniform((uint32_t)warp);      // provably warp-uniform copy
@@ -174,11 +188,13 @@ unit_bwd_st_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
   if (warp == 0) tmem_alloc<TMEM_COLS>(tmem_ptr);
   if (tid == 0) {
 #pragma unroll
-    for (int i = 0; i < 6; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
+    mbar_init(&bars[5], NTG / 32);
+    mbar_init(&bars[6], NT / 32);
     mbar_fence_init();
     tma_prefetch_desc(&tmap); tma_prefetch_desc(&tmap_du); tma_prefetch_desc(&tmap_zo);
   }
-  for (int i = tid; i < 64 * 64; i += NT) {
+  for (int i = tid; i < 64 * 64; i += NTT) {
     const int co = i / 64, ci = i % 64;
     const float w = __ldg(a.w1 + i);
     const uint32_t o1 = sw128_offset(64, co, ci);     // GEMM1: B[n=co][k=ci]
@@ -188,7 +204,7 @@ unit_bwd_st_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     *reinterpret_cast<uint32_t*>(smem + Off::B2HI + o2) = tf32_hi(w);
     *reinterpret_cast<uint32_t*>(smem + Off::B2LO + o2) = tf32_lo(w);
   }
-  for (int i = tid; i < 9 * 64; i += NT) sW2[i] = __ldg(a.w2 + (i % 64) * 9 + i / 64);
+  for (int i = tid; i < 9 * 64; i += NTT) sW2[i] = __ldg(a.w2 + (i % 64) * 9 + i / 64);
   if (tid < 64) {
     sB1[tid] = __ldg(a.b1 + tid);
     const Coef4 ki = bn_coef_tc(a.bna, tid);
@@ -223,46 +239,6 @@ unit_bwd_st_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
   const uint64_t dAhi = make_desc_sw128_mnmajor(smem_u32(smem + Off::RAW), 16384, 512, 1);
   const uint64_t dAlo = make_desc_sw128_mnmajor(smem_u32(smem + Off::AL), 16384, 512, 1);
 
-  // ---- persistent accumulators
-  // depthwise-backward stage: thread -> (channel pair q2, column group cg of 5 interior columns);
-  // the g rows r-1 and r of its 7 columns stay in registers while the strip streams by
-  const int q2 = tid & 31, cg = tid >> 5;
-  float2 w2r[9], gw2[9];
-#pragma unroll
-  for (int k = 0; k < 9; ++k) {
-    w2r[k] = *reinterpret_cast<const float2*>(sW2 + k * 64 + q2 * 2);
-    gw2[k] = make_float2(0.f, 0.f);
-  }
-  float2 gb2 = make_float2(0.f, 0.f), gb1 = gb2;
-  float2 wa[7], wb[7];
-#pragma unroll
-  for (int d = 0; d < 7; ++d) { wa[d] = make_float2(0.f, 0.f); wb[d] = wa[d]; }
-  // byte offsets of the thread's 7 g columns inside a tile row of the TMA layout
-  // ([ch block][pixel][128 B], 16-byte chunks ^ (pixel & 7)) without the row term
-  int gcolx[7];
-#pragma unroll
-  for (int d = 0; d < 7; ++d) { const int c = cg * 5 + d; gcolx[d] = c < SWH ? c : SWH - 1; }
-  // dW1: thread (TMEM lane `row`, column half) accumulates row (row & 63) of dW1, input channels
-  // half*32 .. +31; lanes 64..127 carry the dy_lo part of the same rows
-  float gw1[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) gw1[j] = 0.f;
-  // g pass: the channel quad of a thread is fixed (256 % 16 == 0): coefficients in registers
-  const float4 cgs = *reinterpret_cast<const float4*>(sCo + (tid & 15) * 4);
-  const float4 cm1 = *reinterpret_cast<const float4*>(sCo + 64 + (tid & 15) * 4);
-  const float4 cmu = *reinterpret_cast<const float4*>(sCo + 192 + (tid & 15) * 4);
-  float4 ck;                                          // rstd * mean(du * zhat)
-  {
-    const float4 m2 = *reinterpret_cast<const float4*>(sCo + 128 + (tid & 15) * 4);
-    const float4 rs = *reinterpret_cast<const float4*>(sCo + 256 + (tid & 15) * 4);
-    ck = make_float4(rs.x * m2.x, rs.y * m2.y, rs.z * m2.z, rs.w * m2.w);
-  }
-  // pooled / up-add routing: thread -> (channel quad eq, pixels tid/16 + 16k)
-  const int eq = tid & 15;
-  float4 sa1 = make_float4(0.f, 0.f, 0.f, 0.f), sa2 = sa1, sb1 = sa1, sb2 = sa1;
-  // statistics of du_in: lane L of a warp owns channel half*32 + L
-  double s1 = 0.0, s2 = 0.0;
-
   // ---- this CTA's share of the global block sequence
   const int g0 = (int)(((long long)blockIdx.x * geo.G) / gridDim.x);
   const int g1 = (int)(((long long)(blockIdx.x + 1) * geo.G) / gridDim.x);
@@ -295,12 +271,119 @@ unit_bwd_st_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     tma_load_4d(dst, m, bar, 0, sx_ * SW - 1, y_, b_);
     tma_load_4d(dst + 16384, m, bar, 32, sx_ * SW - 1, y_, b_);
   };
+  if (warp_u >= NT / 32) {
+    // ================================================================ g warps =====================
+    // g = gamma*rstd*(du - mean(du) - zhat*mean(du*zhat)) in place over the du tile (TMA), z_out read
+    // straight from global memory (its rows are pulled into L2 one step ahead).  The g tile holds image
+    // rows y0+1 .. y0+RB (one row below the block's own rows), exact 0 outside the image.  The loop
+    // runs one step ahead of the main warps: it hands a finished tile over through bars[5] and refills
+    // the buffer with the next step's du as soon as the main warps have read it (bars[6]).
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+    const int gt = tid - NT, glane = gt & 31;
+    const int ch = gt & 15;
+    const float4 cgs = *reinterpret_cast<const float4*>(sCo + ch * 4);
+    const float4 cm1 = *reinterpret_cast<const float4*>(sCo + 64 + ch * 4);
+    const float4 cmu = *reinterpret_cast<const float4*>(sCo + 192 + ch * 4);
+    float4 ck;                                          // rstd * mean(du * zhat)
+    {
+      const float4 m2 = *reinterpret_cast<const float4*>(sCo + 128 + ch * 4);
+      const float4 rs = *reinterpret_cast<const float4*>(sCo + 256 + ch * 4);
+      ck = make_float4(rs.x * m2.x, rs.y * m2.y, rs.z * m2.z, rs.w * m2.w);
+    }
+    Step st = first_step();
+    int gcur = g0;
+    uint32_t it = 0;
+    bool galive = alive;
+    if (gt == 0 && st.valid && galive) issue(&tmap_du, sG, &bars[4], st.sx, st.blk * RB + 1, st.b);
+    while (st.valid && galive) {
+      const Step nx = next_step(st, gcur);
+      const int y0 = st.blk * RB, x0 = st.sx * SW;
+      const float* zo_img = a.zout + (long long)st.b * a.H * a.W * C64;
+      if (nx.valid && gt < 32)       // z_out rows of the next step -> L2
+        l2_prefetch_tile<C64>(a.zout + (long long)nx.b * a.H * a.W * C64, a.H, a.W, nx.blk * RB + 1,
+                              nx.blk * RB + 1 + RB, nx.sx * SW - 1, nx.sx * SW - 1 + SWH, glane);
+      if (!mbar_wait(&bars[4], it & 1)) { galive = false; if (glane == 0) atomicExch(status, 14); }
+      if (galive) {
+        int py = 0, px = gt >> 4;          // tile pixel (gt >> 4) + 8 k
+#pragma unroll 1
+        for (int k0 = 0; k0 < 16; k0 += 4) {
+          float4 zv[4];
+          bool ok[4];
+          int pixs[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            while (px >= SWH) { px -= SWH; ++py; }
+            pixs[u] = (gt >> 4) + 8 * (k0 + u);
+            const int gy = y0 + 1 + py, gx = x0 - 1 + px;
+            ok[u] = py < RB && gy >= 0 && gy < a.H && gx >= 0 && gx < a.W;
+            zv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok[u]) zv[u] = __ldg(reinterpret_cast<const float4*>(zo_img + ((long long)gy * a.W + gx) * C64 + ch * 4));
+            px += 8;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            float* gp = const_cast<float*>(rchunk(sG, pixs[u], ch));
+            float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok[u]) {
+              const float4 d = *reinterpret_cast<const float4*>(gp);
+              const float4 z = zv[u];
+              g.x = cgs.x * (d.x - cm1.x - (z.x - cmu.x) * ck.x);
+              g.y = cgs.y * (d.y - cm1.y - (z.y - cmu.y) * ck.y);
+              g.z = cgs.z * (d.z - cm1.z - (z.z - cmu.z) * ck.z);
+              g.w = cgs.w * (d.w - cm1.w - (z.w - cmu.w) * ck.w);
+            }
+            *reinterpret_cast<float4*>(gp) = g;
+          }
+        }
+      }
+      fence_proxy_async_smem();      // generic writes of g precede the TMA refill of the buffer
+      __syncwarp();
+      if (glane == 0) mbar_arrive(&bars[5]);
+      // the main warps have rolled / consumed this tile: refill with the next step's du
+      if (galive && !mbar_wait(&bars[6], it & 1)) { galive = false; if (glane == 0) atomicExch(status, 17); }
+      if (gt == 0 && nx.valid && galive) issue(&tmap_du, sG, &bars[4], nx.sx, nx.blk * RB + 1, nx.b);
+      if (!st.prime) ++gcur;
+      ++it;
+      st = nx;
+    }
+  } else {
+  // ================================================================== main warps ====================
+  // register pool of the CTA: 12 warps x 168 registers (what __launch_bounds__(384, 1) compiles to) = 64 512;
+  // the four g warps keep 64 each, which leaves 8 warps x 220: the request must not exceed that (a larger
+  // one blocks forever), and setmaxnreg takes multiples of 8
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+  // ---- persistent accumulators
+  // depthwise-backward stage: thread -> (channel pair q2, column group cg of 5 interior columns);
+  // the g rows r-1 and r of its 7 columns stay in registers while the strip streams by
+  const int q2 = tid & 31, cg = tid >> 5;
+  float2 w2r[9], gw2[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    w2r[k] = *reinterpret_cast<const float2*>(sW2 + k * 64 + q2 * 2);
+    gw2[k] = make_float2(0.f, 0.f);
+  }
+  float2 gb2 = make_float2(0.f, 0.f), gb1 = gb2;
+  float2 wa[7], wb[7];
+#pragma unroll
+  for (int d = 0; d < 7; ++d) { wa[d] = make_float2(0.f, 0.f); wb[d] = wa[d]; }
+  // byte offsets of the thread's 7 g columns inside a tile row of the TMA layout
+  // ([ch block][pixel][128 B], 16-byte chunks ^ (pixel & 7)) without the row term
+  int gcolx[7];
+#pragma unroll
+  for (int d = 0; d < 7; ++d) { const int c = cg * 5 + d; gcolx[d] = c < SWH ? c : SWH - 1; }
+  // dW1: thread (TMEM lane `row`, column half) accumulates row (row & 63) of dW1, input channels
+  // half*32 .. +31; lanes 64..127 carry the dy_lo part of the same rows
+  float gw1[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) gw1[j] = 0.f;
+  // pooled / up-add routing: thread -> (channel quad eq, pixels tid/16 + 16k)
+  const int eq = tid & 15;
+  float4 sa1 = make_float4(0.f, 0.f, 0.f, 0.f), sa2 = sa1, sb1 = sa1, sb2 = sa1;
+  // statistics of du_in: lane L of a warp owns channel half*32 + L
+  double s1 = 0.0, s2 = 0.0;
+
   Step st = first_step();
   int gcur = g0;
-  if (tid == 0 && st.valid && alive) {
-    issue(&tmap_du, sG, &bars[4], st.sx, st.blk * RB + 1, st.b);
-    issue(&tmap_zo, sY, &bars[5], st.sx, st.blk * RB + 1, st.b);
-  }
   uint32_t it_s = 0, it_r = 0;        // completed steps / real blocks (barrier phases)
   const int hy = row / SWH, hx = row - hy * SWH;       // tile pixel of this thread (TMEM lane)
   while (st.valid && alive) {
@@ -367,35 +450,11 @@ unit_bwd_st_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         *reinterpret_cast<float4*>(raw + zoff(pix, ch)) = v;
       }
     }
-    if (!mbar_wait(&bars[4], phs)) { alive = false; if (lane == 0) atomicExch(status, 14); }
-    if (alive && !mbar_wait(&bars[5], phs)) { alive = false; if (lane == 0) atomicExch(status, 15); }
     PT(0);
-    if (alive) {
-      // g = gamma*rstd*(du - mean(du) - zhat*mean(du*zhat)) in place; the g tile holds image rows
-      // y0+1 .. y0+RB (one row below the block's own rows), exact 0 outside the image
-      int py = 0, px = tid >> 4;          // tile pixel (tid >> 4) + 16 k without a division
-#pragma unroll 4
-      for (int k = 0; k < 128 * 16 / NT; ++k, px += 16) {
-        while (px >= SWH) { px -= SWH; ++py; }
-        const int pix = (tid >> 4) + 16 * k, ch = tid & 15;
-        const int gy = y0 + 1 + py, gx = x0 - 1 + px;
-        float* gp = const_cast<float*>(rchunk(sG, pix, ch));
-        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (py < RB && gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) {
-          const float4 d = *reinterpret_cast<const float4*>(gp);
-          const float4 z = *reinterpret_cast<const float4*>(rchunk(sY, pix, ch));
-          g.x = cgs.x * (d.x - cm1.x - (z.x - cmu.x) * ck.x);
-          g.y = cgs.y * (d.y - cm1.y - (z.y - cmu.y) * ck.y);
-          g.z = cgs.z * (d.z - cm1.z - (z.z - cmu.z) * ck.z);
-          g.w = cgs.w * (d.w - cm1.w - (z.w - cmu.w) * ck.w);
-        }
-        *reinterpret_cast<float4*>(gp) = g;
-      }
-    }
     PT(1);
     if (st.prime) {
       // ---- priming step: only roll the g window over the rows of this block
-      __syncthreads();
+      if (!mbar_wait(&bars[5], phs)) { alive = false; if (lane == 0) atomicExch(status, 15); }
       if (alive) {
 #pragma unroll
         for (int ii = 0; ii < RBT; ++ii) {
@@ -407,14 +466,12 @@ unit_bwd_st_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
           }
         }
       }
-      fence_proxy_async_smem();
-      __syncthreads();
-      if (tid == 0 && nx.valid && alive) {
-        issue(&tmap_du, sG, &bars[4], nx.sx, nx.blk * RB + 1, nx.b);
-        issue(&tmap_zo, sY, &bars[5], nx.sx, nx.blk * RB + 1, nx.b);
-        if (MODE == 0) issue(&tmap, raw, &bars[0], nx.sx, nx.blk * RB, nx.b);   // the real block that follows
-      }
-      alive = __syncthreads_and(alive ? 1 : 0) != 0;
+      fence_proxy_async_smem();      // generic reads of the g buffer precede its TMA refill
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[6]);
+      if (MODE == 0 && tid == 0 && nx.valid && alive)
+        issue(&tmap, raw, &bars[0], nx.sx, nx.blk * RB, nx.b);   // the real block that follows
+      alive = msync_and(alive);
       ++it_s;
       st = nx;
       continue;
@@ -422,7 +479,7 @@ unit_bwd_st_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     if (MODE == 0) {
       if (alive && !mbar_wait(&bars[0], phr)) { alive = false; if (lane == 0) atomicExch(status, 11); }
     } else {
-      __syncthreads();      // operand a staged by all threads
+      msync();      // operand a staged by all threads
     }
     PT(2);
 
@@ -485,7 +542,7 @@ unit_bwd_st_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
       }
       if (g16 == 1) fence_proxy_async_smem();   // a_hi / a_lo (generic writes) are read by MMA 3
       tc_fence_before();
-      alive = __syncthreads_and(alive ? 1 : 0) != 0;
+      alive = msync_and(alive);
       if (alive) issue_mma1(g16);       // ---- T2: MMA 1   D1 = a W1^T
     }
     PT(3);
@@ -514,7 +571,8 @@ unit_bwd_st_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
       }
     }
     tc_fence_before();
-    __syncthreads();
+    msync();
+    if (alive && !mbar_wait(&bars[5], phs)) { alive = false; if (lane == 0) atomicExch(status, 15); }   // g of this step
     PT(5);
 
     // ---- T4: depthwise backward: dy in place over y, dW2, db2, db1.  New g row r+1 (tile row ii)
@@ -562,8 +620,9 @@ unit_bwd_st_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
       }
     }
     fence_proxy_async_smem();      // generic accesses to the g buffer precede its TMA refill
-    __syncthreads();
-    if (tid == 0 && nx.valid && alive) issue(&tmap_du, sG, &bars[4], nx.sx, nx.blk * RB + 1, nx.b);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&bars[6]);      // the g warps may load the next step's du
+    msync();
     PT(6);
 
     // ---- T5 / T6: dy rows -> hi/lo -> TMEM (A columns are free: MMA 1 completed), in two halves with
@@ -601,11 +660,11 @@ unit_bwd_st_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     };
     if (alive) { convert_dy(0); tmem_wait_st(); }
     tc_fence_before();
-    alive = __syncthreads_and(alive ? 1 : 0) != 0;
+    alive = msync_and(alive);
     if (alive) issue_mma2(0, false);
     if (alive) { convert_dy(1); tmem_wait_st(); }
     tc_fence_before();
-    alive = __syncthreads_and(alive ? 1 : 0) != 0;
+    alive = msync_and(alive);
     if (alive) issue_mma2(1, true);
     PT(7);
     // dy^T for MMA 3 (staged while the second MMA 2 batch runs): this thread's TMEM lane is output
@@ -636,7 +695,7 @@ unit_bwd_st_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     }
     fence_proxy_async_smem();      // y / dy (generic accesses) precede the TMA refill of that buffer
     tc_fence_before();
-    alive = __syncthreads_and(alive ? 1 : 0) != 0;
+    alive = msync_and(alive);
     if (alive && warp_u == 0) {
       if (elect_one_b()) {
         tc_fence_after();
@@ -653,8 +712,6 @@ unit_bwd_st_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
       }
       __syncwarp();
     }
-    // every warp is done reading y / dy: refill that buffer with the next step's z_out
-    if (tid == 32 && nx.valid && alive) issue(&tmap_zo, sY, &bars[5], nx.sx, nx.blk * RB + 1, nx.b);
     if (alive && !mbar_wait(&bars[2], phr)) { alive = false; if (lane == 0) atomicExch(status, 13); }
     tc_fence_after();
     PT(8);
@@ -689,7 +746,7 @@ unit_bwd_st_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                             __uint_as_float(hv[c4 * 4 + 2]), __uint_as_float(hv[c4 * 4 + 3]));
         }
       }
-      __syncthreads();
+      msync();
       if (alive) {
         const float4 sc = *reinterpret_cast<const float4*>(sCa + eq * 4);
         const float4 sh = *reinterpret_cast<const float4*>(sCa + 64 + eq * 4);
@@ -866,7 +923,7 @@ unit_bwd_st_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     // next real block lands behind its g pass (a priming step in between issues it itself)
     fence_proxy_async_smem();
     tc_fence_before();
-    alive = __syncthreads_and(alive ? 1 : 0) != 0;
+    alive = msync_and(alive);
     if (MODE == 0 && tid == 0 && nx.valid && !nx.prime && alive) issue(&tmap, raw, &bars[0], nx.sx, nx.blk * RB, nx.b);
     ++it_s; ++it_r;
     st = nx;
@@ -881,15 +938,15 @@ unit_bwd_st_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
   {
     constexpr int NW1 = 64 * 64, NP = NW1 + 11 * 64;
     float* sRed = reinterpret_cast<float*>(raw);       // tile buffers are free (no TMA in flight)
-    __syncthreads();
+    msync();
     for (int i = tid; i < NP; i += NT) sRed[i] = 0.f;
-    __syncthreads();
+    msync();
     // TMEM lane `row` holds row (row & 63) of dW1 (hi part on lanes < 64, lo part above)
     if (row < 64) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) sRed[row * 64 + half * 32 + j] = gw1[j];
     }
-    __syncthreads();
+    msync();
     if (row >= 64) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) sRed[(row - 64) * 64 + half * 32 + j] += gw1[j];
@@ -904,7 +961,7 @@ unit_bwd_st_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     }
     sStage[(cg * 11 + 9) * 64 + q2 * 2] = gb2.x; sStage[(cg * 11 + 9) * 64 + q2 * 2 + 1] = gb2.y;
     sStage[(cg * 11 + 10) * 64 + q2 * 2] = gb1.x; sStage[(cg * 11 + 10) * 64 + q2 * 2 + 1] = gb1.y;
-    __syncthreads();
+    msync();
     for (int i = tid; i < 11 * 64; i += NT) {
       const int v = i / 64, ch = i % 64;
       float t = 0.f;
@@ -914,7 +971,7 @@ unit_bwd_st_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
       else if (v == 9) sRed[NW1 + 640 + ch] = t;
       else sRed[NW1 + ch] = t;
     }
-    __syncthreads();
+    msync();
     float* dst = a.partial + (long long)blockIdx.x * kPartialStride;
     for (int i = tid; i < NP; i += NT) dst[i] = sRed[i];
   }
@@ -938,6 +995,7 @@ unit_bwd_st_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
       }
     }
   }
+  }      // main warps
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc<TMEM_COLS>(tbase);
@@ -945,28 +1003,7 @@ unit_bwd_st_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
 
 }  // namespace
 
-int unit_bwd_st_supported(int cin, int cout, int mode, int has_bn, int H, int W) {
-  if (!(cin == 64 && cout == 64 && mode >= 0 && mode <= 2 && has_bn && tma_encode_fn() != nullptr)) return 0;
-  const int nsx = (W + 39) / 40, SW = (W + nsx - 1) / nsx;
-  if (mode == 2 && ((SW & 1) || (H & 1))) return 0;     // up-add children pair up inside a block
-  return 1;
-}
-
-// Measured on B200 (bs 256, profiles/r2_*): the strips win where a strip is long (H >= 40: 0.87 vs
-// 1.07 ms at 80x80, 0.255 vs 0.296 ms at 40x40); short strips pay one priming step per 4..7 blocks and
-// the up-add units run 2-row blocks (84 of 128 lanes), where the halo tiles of unit_bwd_tc.cu are as good.
-int unit_bwd_st_preferred(int mode, int H, int W) {
-  (void)W;
-  if (mode == 2) return 0;
-  if (mode == 1) return H >= 20;
-  return H >= 40;
-}
-
-cudaError_t launch_unit_bwd_st(int mode, const UnitBwdArgs& a, int num_sms, int* status, cudaStream_t s) {
-  {   // development knob, read once: the variant with the g pass on dedicated warps
-    static const int gw = [] { const char* e = getenv("YUNET_ST_GW"); return e ? atoi(e) : 0; }();
-    if (gw == 1) return launch_unit_bwd_st_gw(mode, a, num_sms, status, s);
-  }
+cudaError_t launch_unit_bwd_st_gw(int mode, const UnitBwdArgs& a, int num_sms, int* status, cudaStream_t s) {
   if (a.dout_batch_stride != (long long)a.H * a.W * C64) return cudaErrorInvalidValue;
   StripB geo;
   geo.nsx = (a.W + 39) / 40;
@@ -992,14 +1029,14 @@ cudaError_t launch_unit_bwd_st(int mode, const UnitBwdArgs& a, int num_sms, int*
   auto go = [&](auto kern) -> cudaError_t {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<grid, NT, smem, s>>>(tm[0], tm[1], tm[2], a, geo, status);
+    kern<<<grid, NTT, smem, s>>>(tm[0], tm[1], tm[2], a, geo, status);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     return launch_reduce_partials(a.partial, grid, 64 * 64 + 11 * 64, a.gw1, s);
   };
-  if (mode == 0) return go(unit_bwd_st_kernel<0, 3>);
-  if (mode == 1) return go(unit_bwd_st_kernel<1, 3>);
-  if (mode == 2) return go(unit_bwd_st_kernel<2, 2>);
+  if (mode == 0) return go(unit_bwd_st_gw_kernel<0, 3>);
+  if (mode == 1) return go(unit_bwd_st_gw_kernel<1, 3>);
+  if (mode == 2) return go(unit_bwd_st_gw_kernel<2, 2>);
   return cudaErrorInvalidValue;
 }
 
