@@ -355,6 +355,35 @@ class YuNet_Head(nn.Module):
         eng = _engine_for(x.backbone, x.neck, self)
         return eng.losses(x.img, gt_bboxes, gt_keypointss)
 
+    # ---- loss (yunet_head.py:418-534) on caller-provided head outputs: what a reference-style
+    # ``forward_train`` (``outs = self(x); self.loss(*outs, gt_bboxes, gt_labels, gt_keypointss,
+    # img_metas)``, yunet_head.py:276-283) or a foreign backbone calls.  SimOTA + the four losses run
+    # in the same two kernels as the fused path; the gradient flows back into the given tensors.
+    def loss(self, cls_scores, bbox_preds, objectnesses, kps_preds, gt_bboxes, gt_labels, gt_kpss,
+             img_metas, gt_bboxes_ignore=None):
+        if self.strides != [8, 16, 32]:
+            raise NotImplementedError('the fused loss is built for strides [8, 16, 32] (configs/yunet_n.py:122)')
+        if gt_kpss is None:
+            raise ValueError('YuNet_Head.loss needs gt_kpss (use_kps=True, configs/yunet_n.py:129)')
+        B = cls_scores[0].shape[0]
+        H, W = cls_scores[0].shape[2] * self.strides[0], cls_scores[0].shape[3] * self.strides[0]
+        dev = cls_scores[0].device
+        if dev.type != 'cuda':
+            raise RuntimeError('YuNet_Head.loss needs CUDA tensors (there is no CPU fallback)')
+
+        def fl(lst, c):     # the reference's permute(0, 2, 3, 1).reshape(B, -1, c) per level, then cat
+            return torch.cat([t.permute(0, 2, 3, 1).reshape(B, -1, c) for t in lst], 1)
+
+        preds = torch.cat([fl(cls_scores, 1), fl(bbox_preds, 4), fl(objectnesses, 1),
+                           fl(kps_preds, 10)], -1).float().contiguous()
+        core = self.__dict__.get('_b200_loss_engine')
+        if core is None or core.device != dev:
+            core = YuNetEngine('yunet_n', device=dev, loss_cfg=self.loss_cfg)
+            self.__dict__['_b200_loss_engine'] = core
+        gt, offs = pack_gt_csr_device(gt_bboxes, gt_kpss, dev)
+        l = _HeadLoss.apply(core, gt, offs, H, W, preds)
+        return dict(loss_cls=l[0], loss_bbox=l[1], loss_obj=l[2], loss_kps=l[3])
+
     # ---- get_bboxes (yunet_head.py:290-374): decode + score filter + NMS on the GPU
     def get_bboxes(self, cls_scores, bbox_preds, objectnesses, kps_preds, img_metas=None, cfg=None,
                    rescale=False, with_nms=True):
@@ -435,6 +464,39 @@ class _FusedLoss(torch.autograd.Function):
         # AccumulateGrad adopts it as ``.grad`` when the gradient was None (zero_grad(set_to_none=True),
         # torch's default) and adds it in place otherwise; the bucket is rewritten by the next backward
         return (None, None, None, None) + glue.grad_views
+
+
+class _HeadLoss(torch.autograd.Function):
+    """``YuNet_Head.loss`` on explicit predictions (B, P, 16): ``yunet_simota_assign`` +
+    ``yunet_loss_grad``; backward returns d loss / d preds (recomputed with the upstream scales when
+    the four losses are not simply summed)."""
+
+    @staticmethod
+    def forward(ctx, core, gt, offs, H, W, preds):
+        assigned, miou, counters = core.assign(preds, gt, offs, H, W)
+        num_total = counters
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            num_total = counters[:1].clone() / dist.get_world_size()   # reduce_mean, yunet_head.py:493-497
+            dist.all_reduce(num_total)
+        losses, d_preds = core.loss_grad(preds, gt, offs, assigned, miou, counters, num_total, H, W)
+        # the engine's buffers are reused by its next call: keep private copies for backward
+        ctx.core, ctx.hw = core, (H, W)
+        ctx.saved = (preds.detach(), gt, offs, assigned.clone(), miou.clone(), counters.clone(),
+                     num_total.clone(), d_preds.clone())
+        out = losses.clone()
+        return out[0], out[1], out[2], out[3]
+
+    @staticmethod
+    def backward(ctx, g_cls, g_bbox, g_obj, g_kps):
+        preds, gt, offs, assigned, miou, counters, num_total, d_preds = ctx.saved
+        scale = [float(g) for g in (g_cls, g_bbox, g_obj, g_kps)]
+        if scale != [1.0, 1.0, 1.0, 1.0]:
+            H, W = ctx.hw
+            _, d = ctx.core.loss_grad(preds, gt, offs, assigned, miou, counters, num_total, H, W,
+                                      loss_scale=scale)
+            d_preds = d.clone()
+        return None, None, None, None, None, d_preds
 
 
 def pack_gt_csr_device(gt_bboxes, gt_keypointss, device):

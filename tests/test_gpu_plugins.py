@@ -160,3 +160,48 @@ def test_assigner_assign_matches_oracle(seed):
     # no ground truth -> everything background, zero overlaps (sim_ota_assigner.py:137-151)
     empty = asg.assign(scores.cuda(), offset_priors.cuda(), decoded.cuda(), gtb[:0].cuda(), gtl[:0].cuda())
     assert int(empty.gt_inds.abs().sum()) == 0 and float(empty.max_overlaps.abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize('arch', ['yunet_n', 'yunet_s'])
+def test_head_loss_on_explicit_outputs_equals_the_fused_forward_train(arch):
+    """``YuNet_Head.loss(*head(feats), gt_bboxes, gt_labels, gt_kpss, img_metas)`` (yunet_head.py:418-534,
+    the call a reference-style ``forward_train`` makes): the losses of the fused ``forward_train`` and,
+    on the same predictions, exactly the losses / d_preds of the engine's assign + loss kernels."""
+    B, size, seed = 4, 320, 0
+    m = _model(arch).train()
+    img = torch.from_numpy(synthetic.make_images(B, size, seed)).cuda()
+    gb, gl, gk = synthetic.make_gt(B, size, seed)
+    gb = [torch.from_numpy(x).cuda() for x in gb]
+    gl = [torch.from_numpy(x).cuda() for x in gl]
+    gk = [torch.from_numpy(x).cuda() for x in gk]
+    fused = m.forward_train(img, [{}] * B, gb, gl, gk)
+    core = plugins._engine_for(m.backbone, m.neck, m.bbox_head).core
+    outs = m.bbox_head(m.extract_feat(img))           # train-mode head maps, four lists of three levels
+    leaves = [[t.detach().clone().requires_grad_() for t in lst] for lst in outs]
+    losses = m.bbox_head.loss(*leaves, gb, gl, gk, [{}] * B)
+    # (two train-mode forwards differ in the last bits of the batch statistics: fp64 atomics)
+    for k in ('loss_cls', 'loss_bbox', 'loss_obj', 'loss_kps'):
+        assert abs(float(losses[k]) - float(fused[k])) <= 1e-4 * max(1.0, abs(float(fused[k]))), k
+    # the engine on the same predictions
+    fl = lambda lst, c: torch.cat([t.permute(0, 2, 3, 1).reshape(B, -1, c) for t in lst], 1)
+    preds = torch.cat([fl(outs[0], 1), fl(outs[1], 4), fl(outs[2], 1), fl(outs[3], 10)], -1).contiguous()
+    gt, offs = plugins.pack_gt_csr_device(gb, gk, preds.device)
+    assigned, miou, counters = core.assign(preds, gt, offs, size, size)
+    l_ref, d_ref = core.loss_grad(preds, gt, offs, assigned, miou, counters, counters, size, size)
+    l_ref, d_ref = l_ref.clone(), d_ref.clone()
+    for i, k in enumerate(('loss_cls', 'loss_bbox', 'loss_obj', 'loss_kps')):
+        assert abs(float(losses[k]) - float(l_ref[i])) <= 1e-6 * max(1.0, abs(float(l_ref[i]))), k
+    sum(losses.values()).backward()
+    off = 0
+    for lvl, s in enumerate((8, 16, 32)):
+        h = w = size // s
+        d = d_ref[:, off:off + h * w].reshape(B, h, w, 16).permute(0, 3, 1, 2)
+        off += h * w
+        for lst, sl in zip(leaves, (slice(0, 1), slice(1, 5), slice(5, 6), slice(6, 16))):
+            assert torch.allclose(lst[lvl].grad, d[:, sl], rtol=1e-6, atol=1e-12), (lvl, sl)
+    # unequal upstream scales re-run the loss kernel with them (loss_cls x 2 here)
+    leaves2 = [[t.detach().clone().requires_grad_() for t in lst] for lst in outs]
+    l2 = m.bbox_head.loss(*leaves2, gb, gl, gk, [{}] * B)
+    (2.0 * l2['loss_cls'] + l2['loss_bbox'] + l2['loss_obj'] + l2['loss_kps']).backward()
+    assert torch.allclose(leaves2[0][0].grad, 2.0 * leaves[0][0].grad, rtol=1e-5, atol=1e-9)
+    assert torch.allclose(leaves2[1][0].grad, leaves[1][0].grad, rtol=1e-5, atol=1e-9)
