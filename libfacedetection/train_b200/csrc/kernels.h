@@ -130,8 +130,6 @@ cudaError_t launch_unit_bwd_tc(int mode, const UnitBwdArgs& a, int num_sms, int*
 int unit_bwd_st_supported(int cin, int cout, int mode, int has_bn, int H, int W);
 int unit_bwd_st_preferred(int mode, int H, int W);   // shapes where it beats the per-tile kernel
 cudaError_t launch_unit_bwd_st(int mode, const UnitBwdArgs& a, int num_sms, int* status, cudaStream_t s);
-// experimental: g pass on dedicated warps (unit_bwd_st_gw.cu), taken by launch_unit_bwd_st when YUNET_ST_GW=1
-cudaError_t launch_unit_bwd_st_gw(int mode, const UnitBwdArgs& a, int num_sms, int* status, cudaStream_t s);
 
 // ---- launchers (kernels_bwd.cu) ----
 cudaError_t launch_unit_bwd(int cin, int cout, int mode, const UnitBwdArgs& a, int num_sms,

@@ -963,10 +963,6 @@ int unit_bwd_st_preferred(int mode, int H, int W) {
 }
 
 cudaError_t launch_unit_bwd_st(int mode, const UnitBwdArgs& a, int num_sms, int* status, cudaStream_t s) {
-  {   // development knob, read once: the variant with the g pass on dedicated warps
-    static const int gw = [] { const char* e = getenv("YUNET_ST_GW"); return e ? atoi(e) : 0; }();
-    if (gw == 1) return launch_unit_bwd_st_gw(mode, a, num_sms, status, s);
-  }
   if (a.dout_batch_stride != (long long)a.H * a.W * C64) return cudaErrorInvalidValue;
   StripB geo;
   geo.nsx = (a.W + 39) / 40;

@@ -462,8 +462,10 @@ class _FusedLoss(torch.autograd.Function):
         core.backward(img, d_preds)
         # every parameter gets a VIEW of the flat gradient bucket (no copies): autograd's
         # AccumulateGrad adopts it as ``.grad`` when the gradient was None (zero_grad(set_to_none=True),
-        # torch's default) and adds it in place otherwise; the bucket is rewritten by the next backward
-        return (None, None, None, None) + glue.grad_views
+        # torch's default) and adds it in place otherwise; the bucket is rewritten by the next backward.
+        # The views must be FRESH objects: AccumulateGrad only steals a gradient nobody else references
+        # (a cached tuple of views makes it clone every one of them).
+        return (None, None, None, None) + glue.fresh_grad_views()
 
 
 class _HeadLoss(torch.autograd.Function):
@@ -535,14 +537,25 @@ class _Glue:
         self.core = YuNetEngine(arch, device=dev, loss_cfg=head.loss_cfg)
         self.modules = {'backbone': backbone, 'neck': neck, 'bbox_head': head}
         self.names = [n for n, _, _ in self.core.param_table]
-        gv = self.core.param_views(self.core.grads)
         mv = self.core.param_views(self.core.momentum_buf)
-        self.grad_views = tuple(gv[k] for k in self.names)        # handed out by every backward
         self.momentum_views = tuple(mv[k] for k in self.names)    # ``SGD.state[p]['momentum_buffer']``
-        self.grad_ptrs = [v.data_ptr() for v in self.grad_views]
         self.momentum_ptrs = [v.data_ptr() for v in self.momentum_views]
+        # the gradient views handed out by every backward: addresses are fixed, the view objects are not
+        table = self.core.param_table
+        self._shapes = [tuple(shape) for _, _, shape in table]
+        self._sizes = [int(np.prod(shape)) for _, _, shape in table]
+        self._dense = all(table[i + 1][1] == table[i][1] + self._sizes[i] for i in range(len(table) - 1)) \
+            and table[0][1] == 0 and table[-1][1] + self._sizes[-1] == self.core.grads.numel()
+        self.grad_ptrs = [self.core.grads.data_ptr() + 4 * off for _, off, _ in table]
         self._adopt()
         _LIVE_GLUES.add(self)
+
+    def fresh_grad_views(self):
+        g = self.core.grads
+        if self._dense:      # one split call instead of a slice per parameter
+            return tuple(v.view(sh) for v, sh in zip(g.split(self._sizes), self._shapes))
+        views = self.core.param_views(g)
+        return tuple(views[k] for k in self.names)
 
     def _named(self):
         p, b = {}, {}

@@ -96,6 +96,7 @@ def test_train_step_through_autograd_and_torch_sgd(arch, seed, opt_cls):
     views = core.param_views(core.grads)
     for k, p in m.named_parameters():
         assert torch.equal(p.grad, views[k]), k
+        assert p.grad.data_ptr() == views[k].data_ptr(), k      # adopted view of the bucket, not a copy
     if opt_cls == 'plugin':
         assert opt._fused_glue() is not None          # the step below is the one-launch path
     opt.step()
