@@ -572,7 +572,9 @@ __global__ void __launch_bounds__(NT, OCC) unit_bwd_kernel(const UnitBwdArgs a) 
 #pragma unroll
             for (int j = 1; j < 4; ++j) { const float vj = comp(v[j], c); if (vj > best) { best = vj; bj = j; } }
             const float hv = best > 0.f ? comp(h, c) : 0.f;
-            const float zb = comp(z[bj], c);
+            float zb = comp(z[0], c);       // z of the winner by selects (a run-time index would put z[] in local memory)
+#pragma unroll
+            for (int j = 1; j < 4; ++j) if (j == bj) zb = comp(z[j], c);
             const float zh = (zb - comp(mu, c)) * comp(rs, c);
             if (c == 0) { sa1.x += hv; sa2.x = fmaf(hv, zh, sa2.x); }
             if (c == 1) { sa1.y += hv; sa2.y = fmaf(hv, zh, sa2.y); }
