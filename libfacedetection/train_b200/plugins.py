@@ -750,10 +750,29 @@ class YuNet(nn.Module):
         return self.simple_test(img, img_metas, **kwargs)
 
     @staticmethod
-    def _parse_losses(losses):                                # base.py:184-217 (single process)
-        loss = sum(v for k, v in losses.items() if 'loss' in k)
-        log_vars = {k: float(v) for k, v in losses.items()}
-        log_vars['loss'] = float(loss)
+    def _parse_losses(losses):                                # base.py:184-217
+        """``(loss, log_vars)``: ``loss`` = sum of the entries whose key contains 'loss' (with autograd
+        history), ``log_vars`` = python floats, averaged over the ranks when a process group is up
+        (base.py:210-214).  The reference all-reduces and ``.item()``s entry by entry; here the entries
+        travel as ONE stacked vector: one collective and one device-to-host read per step."""
+        from collections import OrderedDict
+        import torch.distributed as dist
+        log_vars = OrderedDict()
+        for name, value in losses.items():
+            if isinstance(value, torch.Tensor):
+                log_vars[name] = value.mean() if value.dim() else value
+            elif isinstance(value, list):
+                log_vars[name] = sum(_l.mean() for _l in value)
+            else:
+                raise TypeError(f'{name} is not a tensor or list of tensors')
+        loss = sum(v for k, v in log_vars.items() if 'loss' in k)
+        log_vars['loss'] = loss
+        vec = torch.stack([v.detach().float() for v in log_vars.values()])
+        if dist.is_available() and dist.is_initialized():
+            vec = vec / dist.get_world_size()
+            dist.all_reduce(vec)
+        for k, x in zip(list(log_vars), vec.tolist()):
+            log_vars[k] = x
         return loss, log_vars
 
     def train_step(self, data, optimizer=None):               # base.py:219-252

@@ -31,7 +31,14 @@ def _worker(rank, world, port, tmp):
         v = 0.9 * v + gi
         w = w - 0.01 * v
         lo, hi = dist_utils.shard_batch(512, rank, world)
-        torch.save(dict(npos=npos, w=w, shard=(lo, hi)), os.path.join(tmp, f'r{rank}.pt'))
+        # plugin-surface logging (mmdet/models/detectors/base.py:184-217): log_vars are rank means, the
+        # loss tensor that is back-propagated stays local
+        from libfacedetection.train_b200 import plugins
+        ls = dict(loss_cls=torch.tensor(1.0 + rank, requires_grad=True), loss_bbox=torch.tensor(2.0 * (rank + 1)),
+                  loss_obj=torch.tensor(0.5), loss_kps=[torch.tensor([1.0, 3.0]) * (rank + 1)], acc=torch.tensor(10.0 * rank))
+        loss, log_vars = plugins.YuNet._parse_losses(ls)
+        torch.save(dict(npos=npos, w=w, shard=(lo, hi), loss=float(loss), log_vars=dict(log_vars),
+                        loss_has_grad=bool(loss.requires_grad)), os.path.join(tmp, f'r{rank}.pt'))
     finally:
         dist.destroy_process_group()
 
@@ -46,6 +53,22 @@ def test_world2_gloo(tmp_path):
     w_ref = torch.ones(1000) - 0.01 * (mean_g + 0.0005)
     assert torch.allclose(r0['w'], w_ref) and torch.equal(r0['w'], r1['w'])
     assert r0['shard'] == (0, 256) and r1['shard'] == (256, 512)
+    # rank 0: 1 + 2 + 0.5 + 2 = 5.5, rank 1: 2 + 4 + 0.5 + 4 = 10.5 ('acc' has no 'loss' in its key)
+    assert r0['loss'] == pytest.approx(5.5) and r1['loss'] == pytest.approx(10.5) and r0['loss_has_grad']
+    assert r0['log_vars'] == r1['log_vars']
+    assert r0['log_vars'] == pytest.approx(dict(loss_cls=1.5, loss_bbox=3.0, loss_obj=0.5, loss_kps=3.0, acc=5.0, loss=8.0))
+    assert list(r0['log_vars']) == ['loss_cls', 'loss_bbox', 'loss_obj', 'loss_kps', 'acc', 'loss']
+
+
+def test_parse_losses_single_process():
+    from libfacedetection.train_b200 import plugins
+    ls = dict(loss_cls=torch.tensor(1.25, requires_grad=True), loss_bbox=torch.tensor(2.0), loss_obj=torch.tensor(0.5),
+              loss_kps=torch.tensor(0.25))
+    loss, log_vars = plugins.YuNet._parse_losses(ls)
+    assert float(loss) == 4.0 and loss.requires_grad
+    assert dict(log_vars) == dict(loss_cls=1.25, loss_bbox=2.0, loss_obj=0.5, loss_kps=0.25, loss=4.0)
+    with pytest.raises(TypeError):
+        plugins.YuNet._parse_losses(dict(loss_x=1.0))
 
 
 def test_single_process_is_identity():
