@@ -505,6 +505,7 @@ int yunet_backward(yunet_ctx* ctx, const float* img, const float* params, const 
       e = st ? launch_unit_bwd_st(u.mode, a, ctx->num_sms, v.status() + 1, s)
           : tc ? launch_unit_bwd_tc(u.mode, a, ctx->num_sms, v.status() + 1, s)
                : launch_unit_bwd(u.cin, u.cout, u.mode, a, ctx->num_sms, s);
+      ctx->launches++;      // every backward launcher is followed by its reduce_partials_kernel
     }
     if (e != cudaSuccess) return fail(ctx, (int)e, "backward: unit %s: %s", u.name.c_str(), cudaGetErrorString(e));
   }
@@ -520,6 +521,7 @@ int yunet_backward(yunet_ctx* ctx, const float* img, const float* params, const 
     a.B = B; a.Hin = H; a.Win = W;
     Scope sc(ctx, s, "bwd:stem", 4.0 * B * (3.0 * H * W + 2.0 * 16.0 * (H / 2) * (W / 2)));
     e = launch_stem_bwd(a, ctx->num_sms, s);
+    ctx->launches++;        // + reduce_partials_kernel
     if (e != cudaSuccess) return cuda_fail(ctx, e, "backward: stem");
   }
   BnFinalizeArgs fa = make_bn_args(p, B, H, W);
