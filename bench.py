@@ -90,11 +90,25 @@ def cpu_reference_steps(arch, sample, size, steps, warmup, seed=0):
     gk = [torch.from_numpy(x) for x in gk]
     mom = {}
 
+    split = dict(forward=0.0, assign_loss=0.0, backward=0.0, sgd=0.0)
+
     def one_step():
+        # the body of oracle.train_forward_backward + sgd_step with a clock between the phases
         t0 = time.perf_counter()
-        _, grads, _, _ = orc.train_forward_backward(img, P, Bf, arch, gb, gl, gk)
+        Pg = {k: v.detach().clone().requires_grad_(True) for k, v in P.items()}
+        outs = orc.model_forward(img, Pg, Bf, arch, training=True)
+        t1 = time.perf_counter()
+        losses, _ = orc.head_loss(*outs, gb, gl, gk, strides=orc.ARCH[arch]['strides'], return_assign=True)
+        total = sum(losses.values())
+        t2 = time.perf_counter()
+        total.backward()
+        grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in Pg.items()}
+        t3 = time.perf_counter()
         orc.sgd_step(P, grads, mom, lr=LR)
-        return time.perf_counter() - t0
+        t4 = time.perf_counter()
+        for k, dt in zip(split, (t1 - t0, t2 - t1, t3 - t2, t4 - t3)):
+            split[k] += dt
+        return t4 - t0
 
     # the per-image SimOTA loop is thousands of tiny ops: more threads than ~32 only add
     # synchronisation cost, so probe a few thread counts (all host cores first) and keep the best
@@ -106,10 +120,12 @@ def cpu_reference_steps(arch, sample, size, steps, warmup, seed=0):
         if best_t is None or dt < best_t:
             best_t, best_n = dt, n
     torch.set_num_threads(best_n)
+    for k in split:
+        split[k] = 0.0
     times = [one_step() for _ in range(steps)]
     ms = 1e3 * float(np.mean(times))
     return dict(value=sample / (ms / 1e3), ms_per_step=ms, cores=cores, threads=best_n,
-                sample=sample)
+                sample=sample, split_ms={k: round(1e3 * v / max(steps, 1), 2) for k, v in split.items()})
 
 
 def cpu_reference_infer(arch, sample, size, steps, warmup):
@@ -393,7 +409,8 @@ def run_reference(args):
         'cpu_baseline': {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'port',
                          'sample': f'{args.cpu_sample} images/step x {args.steps} steps, torch '
                                    f'{torch.__version__} CPU, best of thread counts up to '
-                                   f'{r["cores"]} (used {r["threads"]})'},
+                                   f'{r["cores"]} (used {r["threads"]})',
+                         'split_ms': r['split_ms']},
         'e2e': {'value': r['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0,
                 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
@@ -682,7 +699,7 @@ def run_ours(args):
                'sample': f'{args.cpu_sample} images/step, 5 timed steps of the oracle train step '
                          f'(fwd+SimOTA+loss+bwd+SGD), torch CPU, best thread count of those probed '
                          f'up to {r["cores"]} host cores (used {r["threads"]})',
-               'ms_per_step': r['ms_per_step']}
+               'ms_per_step': r['ms_per_step'], 'split_ms': r['split_ms']}
 
     # ---------------- the other BASELINE configs and the plugin-surface step, same process (N = 1)
     extra, e2e_plugin = None, None
