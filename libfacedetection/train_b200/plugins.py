@@ -661,7 +661,8 @@ class SGD(torch.optim.SGD):
         if len(self.param_groups) != 1:
             return None
         g = self.param_groups[0]
-        if g.get('dampening', 0) != 0 or g.get('nesterov', False) or g.get('maximize', False):
+        if g.get('dampening', 0) != 0 or g.get('nesterov', False) or g.get('maximize', False) or \
+                g.get('differentiable', False) or isinstance(g['lr'], torch.Tensor):
             return None
         ps = g['params']
         glue = getattr(self, '_b200_glue_ref', None)

@@ -198,9 +198,9 @@ def test_fused_sgd_equals_torch_sgd_and_shares_the_momentum_state():
 
 def test_fused_sgd_falls_back_to_the_stock_step():
     # a None gradient, a gradient in foreign storage, several groups, nesterov: torch.optim.SGD.step
-    for case in ('none_grad', 'foreign_grad', 'two_groups', 'nesterov'):
+    for case in ('none_grad', 'foreign_grad', 'two_groups', 'nesterov', 'tensor_lr'):
         ga, gb = _StubGlue(SHAPES), _StubGlue(SHAPES)
-        kw = dict(KW, nesterov=True) if case == 'nesterov' else KW
+        kw = dict(KW, nesterov=True) if case == 'nesterov' else dict(KW, lr=torch.tensor(0.01)) if case == 'tensor_lr' else KW
         if case == 'two_groups':
             mk = lambda ps: [dict(params=ps[:2]), dict(params=ps[2:], weight_decay=0.0)]
         else:
