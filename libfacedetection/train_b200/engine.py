@@ -81,10 +81,11 @@ class YuNetEngine:
         from . import export
         return export.cpp_data(self.state_dict(), self.arch)
 
-    def export_onnx(self, height=640, width=640):
-        """Serialized 12-output ONNX model (``tools/yunet2onnx.py`` graph, BatchNorm folded)."""
+    def export_onnx(self, height=640, width=640, dynamic=False):
+        """Serialized 12-output ONNX model (``tools/yunet2onnx.py`` graph, BatchNorm folded);
+        ``dynamic=True``: the tool's ``--dynamic-export`` (batch / height / width axes)."""
         from . import export
-        return export.onnx_model(self.state_dict(), self.arch, height, width)
+        return export.onnx_model(self.state_dict(), self.arch, height, width, dynamic=dynamic)
 
     # ------------------------------------------------------------------ parameters
     def param_views(self, bucket=None):

@@ -183,15 +183,21 @@ def _node(op, inputs, outputs, name, **attrs):
 
 
 def _value_info(name, shape):
-    """ValueInfoProto(name=1, type=2{tensor_type=1{elem_type=1, shape=2{dim=1{dim_value=1}}}})."""
-    dims = b''.join(_f_bytes(1, _f_varint(1, d)) for d in shape)
+    """ValueInfoProto(name=1, type=2{tensor_type=1{elem_type=1, shape=2{dim=1{dim_value=1 | dim_param=2}}}});
+    a ``str`` entry of ``shape`` is a symbolic dimension (``dim_param``), an ``int`` a fixed one."""
+    dims = b''.join(_f_bytes(1, _f_bytes(2, d) if isinstance(d, str) else _f_varint(1, d)) for d in shape)
     ttype = _f_varint(1, 1) + _f_bytes(2, dims)
     return _f_bytes(1, name) + _f_bytes(2, _f_bytes(1, ttype))
 
 
-def onnx_model(sd, arch='yunet_n', height=320, width=320, opset=11):
+def onnx_model(sd, arch='yunet_n', height=320, width=320, opset=11, dynamic=False):
     """Serialized ONNX ModelProto of the detector's export graph for a fixed ``(1, 3, H, W)`` input;
-    outputs ``cls_8, cls_16, cls_32, obj_*, bbox_*, kps_*`` like ``tools/yunet2onnx.py:86-93``."""
+    outputs ``cls_8, cls_16, cls_32, obj_*, bbox_*, kps_*`` like ``tools/yunet2onnx.py:86-93``.
+    ``dynamic=True`` is the tool's ``--dynamic-export`` (``tools/yunet2onnx.py:97-100``, the shipped
+    ``onnx/yunet_*_dynamic.onnx``): input axes ``{0: 'batch', 2: 'height', 3: 'width'}``, output axes
+    ``{0: 'batch', 1: 'dim'}``; the graph itself is shape-agnostic (convolutions, 2x2 pools, scale-2 nearest
+    resize), only the flattening ``Reshape`` takes the batch from its input (target shape ``[0, -1, C]``)
+    instead of the constant 1."""
     a = ARCHS[arch] if isinstance(arch, str) else arch
     units = {u['name']: u for u in walk_units(sd, arch)}
     nodes, inits = [], []
@@ -261,18 +267,18 @@ def onnx_model(sd, arch='yunet_n', height=320, width=320, opset=11):
             t = fresh('nhwc')
             nodes.append(_node('Transpose', [y], [t], t, perm=[0, 2, 3, 1]))
             shp = f'shape_{branch}_{i}'
-            inits.append(_tensor(shp, np.array([1, -1, nch], np.int64)))
+            inits.append(_tensor(shp, np.array([0 if dynamic else 1, -1, nch], np.int64)))
             name = f'{branch}_{strides[i]}'
             r = name if not sig else fresh('flat')
             nodes.append(_node('Reshape', [t, shp], [r], r))
             if sig:
                 nodes.append(_node('Sigmoid', [r], [name], name))
             hw = (height // strides[i]) * (width // strides[i])
-            graph_outputs.append(_value_info(name, [1, hw, nch]))
+            graph_outputs.append(_value_info(name, ['batch', 'dim', nch] if dynamic else [1, hw, nch]))
     # GraphProto: node=1, name=2, initializer=5, input=11, output=12
     graph = b''.join(_f_bytes(1, n) for n in nodes) + _f_bytes(2, 'yunet_b200')
     graph += b''.join(_f_bytes(5, t) for t in inits)
-    graph += _f_bytes(11, _value_info('input', [1, 3, height, width]))
+    graph += _f_bytes(11, _value_info('input', ['batch', 3, 'height', 'width'] if dynamic else [1, 3, height, width]))
     graph += b''.join(_f_bytes(12, o) for o in graph_outputs)
     # ModelProto: ir_version=1, producer_name=2, graph=7, opset_import=8{version=2}
     return (_f_varint(1, 6) + _f_bytes(2, 'libfacedetection.train_b200') + _f_bytes(7, graph) +
@@ -289,6 +295,8 @@ def main(argv=None):
     ap.add_argument('--cpp', default=None, help='write facedetectcnn-data.cpp here')
     ap.add_argument('--onnx', default=None, help='write the 12-output ONNX model here')
     ap.add_argument('--shape', type=int, nargs=2, default=[640, 640], help='ONNX input height width')
+    ap.add_argument('--dynamic-export', action='store_true',
+                    help='ONNX with dynamic batch / height / width axes (tools/yunet2onnx.py --dynamic-export)')
     args = ap.parse_args(argv)
     if args.checkpoint.endswith('.npz'):
         sd = dict(np.load(args.checkpoint))
@@ -300,7 +308,7 @@ def main(argv=None):
             f.write(cpp_data(sd, args.arch))
     if args.onnx:
         with open(args.onnx, 'wb') as f:
-            f.write(onnx_model(sd, args.arch, args.shape[0], args.shape[1]))
+            f.write(onnx_model(sd, args.arch, args.shape[0], args.shape[1], dynamic=args.dynamic_export))
     return 0
 
 
