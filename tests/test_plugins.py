@@ -244,3 +244,22 @@ def test_optimizer_registry_builds_the_fused_sgd_from_the_reference_config():
     opt = plugins.OPTIMIZERS.build(dict(type='SGD', lr=0.01, momentum=0.9, weight_decay=0.0005),
                                    default_args=dict(params=ga.params))
     assert type(opt) is plugins.SGD and isinstance(opt, torch.optim.SGD)
+
+
+def test_device_side_gt_packing_equals_the_host_packer_incl_empty_images():
+    """``pack_gt_csr_device`` (torch ops, any device) == ``synthetic.pack_gt_csr`` (numpy), with images
+    without faces given as (0, 4) / (0, 5, 3) or as bare empty tensors."""
+    from libfacedetection.train_b200 import synthetic
+    gb, gl, gk = synthetic.make_gt(6, 320, 3)
+    gb[2], gk[2] = gb[2][:0], gk[2][:0]                       # an image without faces, shaped (0, 4) / (0, 5, 3)
+    ref_gt, ref_offs = synthetic.pack_gt_csr(gb, gk)
+    tb = [torch.from_numpy(x) for x in gb]
+    tk = [torch.from_numpy(x) for x in gk]
+    gt, offs = plugins.pack_gt_csr_device(tb, tk, torch.device('cpu'))
+    assert torch.equal(offs, torch.from_numpy(ref_offs)) and offs.dtype == torch.int32
+    assert torch.equal(gt, torch.from_numpy(ref_gt)) and gt.dtype == torch.float32
+    tb[2], tk[2] = torch.zeros(0), torch.zeros(0)             # ... or as bare empty tensors
+    gt2, offs2 = plugins.pack_gt_csr_device(tb, tk, torch.device('cpu'))
+    assert torch.equal(gt2, gt) and torch.equal(offs2, offs)
+    gt0, offs0 = plugins.pack_gt_csr_device([torch.zeros(0, 4)] * 3, [torch.zeros(0, 5, 3)] * 3, torch.device('cpu'))
+    assert gt0.shape == (0, 19) and offs0.tolist() == [0, 0, 0, 0]
