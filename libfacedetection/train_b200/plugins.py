@@ -80,7 +80,7 @@ def register_into_mmdet(force=True):
     try:    # mmcv.runner.optimizer.builder registers the torch optimizers under their class names
         from mmcv.runner.optimizer.builder import OPTIMIZERS as MM_OPTIMIZERS
         MM_OPTIMIZERS.register_module(name='SGD', force=force, module=SGD)
-    except ImportError:
+    except (ImportError, AttributeError, TypeError):     # an mmcv without that module / a partial stub
         pass
 
 

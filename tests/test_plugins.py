@@ -106,6 +106,10 @@ def test_register_into_mmdet_builds_the_plugins_from_the_reference_config():
         asg = build_assigner(cfg.model.train_cfg.assigner)
         assert type(asg) is plugins.SimOTAAssigner and callable(asg.assign)
         assert asg.center_radius == 2.5 and asg.candidate_topk == 10
+        # optimizer = dict(type='SGD', ...) (configs/yunet_n.py:1) resolves to the fused subclass
+        from mmcv.runner.optimizer.builder import OPTIMIZERS as MM_OPT
+        assert MM_OPT.get('SGD') is plugins.SGD and issubclass(MM_OPT.get('SGD'), torch.optim.SGD)
+        assert cfg.optimizer['type'] == 'SGD'
     finally:
         for k, v in saved.items():
             MODELS.register_module(name=k, force=True, module=v)
